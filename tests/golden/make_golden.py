@@ -1,0 +1,193 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference at /root/reference.
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python tests/golden/make_golden.py
+Every fixture is produced by reference code (imported through oracle/ref_shims.py) and, in the
+same run, compared with the oracle restatement (oracle/p2s_oracle.py); the script fails if
+they disagree, so a committed fixture certifies "oracle == reference" on that input.
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings('ignore')
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+ref_shims.install()
+import torch  # noqa: E402
+from oracle import p2s_oracle as orc  # noqa: E402
+from points2surf_b200 import synth  # noqa: E402
+
+from source import sdf as ref_sdf  # noqa: E402
+from source import sdf_nn as ref_sdf_nn  # noqa: E402
+from source import data_loader as ref_dl  # noqa: E402
+from source.points_to_surf_model import PointsToSurfModel  # noqa: E402
+
+torch.set_grad_enabled(False)
+MODEL_SEEDS = {'vanilla': 6, 'max': 4, 'uniform': 8}
+
+
+def ref_model(variant, seed, fc4_bias=None):
+    v = synth.VARIANTS[variant]
+    m = PointsToSurfModel(net_size_max=1024, num_points=300, output_dim=2,
+                          use_point_stn=v['use_point_stn'], use_feat_stn=1, sym_op='max',
+                          use_query_point=True, sub_sample_size=1000, do_augmentation=False,
+                          single_transformer=0, shared_transformation=v['shared_transformer'])
+    sd = synth.make_state_dict(variant, seed)
+    if fc4_bias is not None:
+        sd['fc4.bias'] = torch.from_numpy(np.asarray(fc4_bias, dtype=np.float32))
+    m.load_state_dict(sd)
+    m.eval()
+    return m
+
+
+def gen_model():
+    for variant, seed in MODEL_SEEDS.items():
+        v = synth.VARIANTS[variant]
+        inp = synth.make_model_inputs(8, seed=100 + seed)
+        # calibrate the output bias on this batch so that the sign classes are mixed
+        # (a rand-init net is otherwise almost always one-signed)
+        x = {k: torch.from_numpy(a.copy()) for k, a in inp.items()}
+        raw = ref_model(variant, seed)(x).numpy()
+        fc4_bias = (synth.make_state_dict_numpy(variant, seed)['fc4.bias'] - np.median(raw, axis=0)).astype(np.float32)
+        m = ref_model(variant, seed, fc4_bias)
+        x = {k: torch.from_numpy(a.copy()) for k, a in inp.items()}
+        logits = m(x).numpy()
+        # the reference centred the sub-sample in place (model.py:303)
+        assert np.allclose(x['pts_sub_sample_ms'].numpy(),
+                           inp['pts_sub_sample_ms'] - inp['imp_surf_query_point_ms'][:, None, :])
+        sd = synth.make_state_dict(variant, seed)
+        sd['fc4.bias'] = torch.from_numpy(fc4_bias)
+        o, aux = orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'],
+                                   inp['imp_surf_query_point_ms'], v['use_point_stn'],
+                                   v['shared_transformer'], return_aux=True)
+        err = np.abs(o - logits).max()
+        assert err < 1e-4, (variant, err)
+        radius = np.linspace(0.05, 0.3, 8).astype(np.float32)
+        pred = torch.from_numpy(logits.copy())
+        mag = ref_sdf_nn.post_process_magnitude(pred[:, 0:1]) * torch.from_numpy(radius).unsqueeze(1)
+        sgn = ref_sdf_nn.post_process_sign(pred[:, 1:2])
+        sdf_ref = (mag.squeeze() * sgn.squeeze()).numpy()
+        assert np.array_equal(orc.post_process(logits, radius), sdf_ref)
+        print('model', variant, 'oracle-vs-reference max abs err', err, 'pos frac', (logits[:, 1] >= 0).mean())
+        np.savez_compressed(os.path.join(HERE, 'model_%s.npz' % variant), seed=seed, input_seed=100 + seed, fc4_bias=fc4_bias,
+                            logits=logits, radius=radius, sdf=sdf_ref,
+                            feat_global_max=aux['feat_global_max'][:2], feat_local_max=aux['feat_local_max'][:2],
+                            input_checksum=np.float64(sum(float(np.abs(a).sum()) for a in inp.values())))
+
+
+def gen_assembly():
+    src = '/root/reference/datasets/abc_minimal/04_pts/00011084_fddd53ce45f640f3ab922328_trimesh_019.xyz.npy'
+    full = np.load(src).astype(np.float32)[:, :3]
+    cloud = full[np.random.RandomState(7).choice(len(full), 6000, replace=False)].copy()
+    res, eps, k, S, seed = 32, 3, 300, 1000, 40938661
+    out = dict(cloud=cloud, res=res, eps=eps, k=k, S=S, seed=seed)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, '04_pts'))
+        np.save(os.path.join(d, '04_pts', 'shape.xyz.npy'), cloud)
+        with open(os.path.join(d, 'testset.txt'), 'w') as f:
+            f.write('shape\n')
+        for uniform in (0, 1):
+            ds = ref_dl.PointcloudPatchDataset(
+                root=d, shape_list_filename='testset.txt', points_per_patch=k, patch_radius=0.0,
+                patch_features=['imp_surf_magnitude', 'imp_surf_sign', 'patch_pts_ids', 'p_index'],
+                epsilon=eps, seed=seed, center='mean', cache_capacity=5, pre_processed_patches=True,
+                query_grid_resolution=res, sub_sample_size=S, reconstruction=True,
+                uniform_subsample=uniform, fixed_subsample=0, num_workers=0)
+            Q = len(ds)
+            qsel = list(range(6)) + [Q // 2, Q - 1]
+            shape = ds.shape_cache.get(0)
+            qpts = shape.imp_surf_query_point_ms
+            # oracle: candidate grid
+            idx = orc.query_grid_indices(cloud, res, eps)
+            assert np.array_equal(idx, orc.query_grid_indices_shifts(cloud, res, eps))
+            assert np.array_equal(orc.volume_space_to_model_space(idx, res).astype(np.float32), qpts)
+            kd = orc.make_kdtree(cloud)
+            rng_o = np.random.RandomState(seed)
+            items, o_items = [], []
+            # the reference consumes its global-sample RNG sequentially: replay queries 0..max in order
+            for qi in range(6):
+                items.append(ds[qi])
+                o_items.append(orc.assemble_query(cloud, kd, qpts[qi], k, S, rng_o, bool(uniform)))
+            for it, oi in zip(items, o_items):
+                assert np.array_equal(it['patch_pts_ps'].numpy(), oi['patch_pts_ps'])
+                assert np.float32(it['patch_radius_ms'].numpy()) == oi['patch_radius_ms']
+                assert np.array_equal(it['pts_sub_sample_ms'].numpy(), oi['pts_sub_sample_ms'])
+                assert np.array_equal(it['imp_surf_query_point_ms'].numpy(), oi['imp_surf_query_point_ms'])
+                bid, bd2 = orc.knn_bruteforce(cloud, oi['imp_surf_query_point_ms'], k)
+                assert set(bid.tolist()) == set(oi['patch_pts_ids'].tolist())
+            tag = 'uni' if uniform else 'wgt'
+            out['query_idx'] = idx.astype(np.int16)
+            out['patch_ids'] = np.stack([oi['patch_pts_ids'] for oi in o_items])
+            out['patch_ps'] = np.stack([it['patch_pts_ps'].numpy() for it in items])
+            out['radius'] = np.array([np.float32(it['patch_radius_ms'].numpy()) for it in items])
+            out['sub_ids_' + tag] = np.stack([oi['sub_sample_ids'] for oi in o_items]).astype(np.int32)
+            print('assembly', tag, 'Q', Q, 'radius', out['radius'][:3])
+    np.savez_compressed(os.path.join(HERE, 'assembly.npz'), **out)
+
+
+def gen_volume():
+    out = {}
+    for name, res, noise in (('sphere', 32, 0.0), ('noisy', 40, 0.15)):
+        cloud = synth.make_cloud('sphere', 3000, seed=5)
+        qpts = ref_sdf.get_voxel_centers_grid_smaller_pc(cloud, res, 3)
+        assert np.array_equal(qpts, orc.query_grid(cloud, res, 3))
+        d = (0.5 - np.linalg.norm(qpts, axis=1)).astype(np.float32)   # + inside (trimesh convention)
+        rng = np.random.RandomState(11)
+        flip = rng.random_sample(len(d)) < noise
+        d[flip] = -d[flip]
+        d[rng.randint(0, len(d), 5)] = 0.0                                  # exact zeros in the band
+        vol_ref = np.zeros((res,) * 3)
+        vol_ref = ref_sdf.add_samples_to_volume(vol_ref, qpts, d)
+        vol_scatter = vol_ref.copy()
+        vol_ref = ref_sdf.propagate_sign(vol_ref, 5, 13)
+        vol_o = np.zeros((res,) * 3)
+        vol_o = orc.add_samples_to_volume(vol_o, qpts, d)
+        assert np.array_equal(vol_o, vol_scatter)
+        vol_o, iters = orc.propagate_sign(vol_o, 5, 13)
+        assert np.array_equal(vol_o, vol_ref), name
+        print('volume', name, 'res', res, 'Q', len(d), 'iterations', iters,
+              'zeros left', int((vol_ref == 0).sum()))
+        out[name + '_res'] = res
+        out[name + '_qpts'] = qpts
+        out[name + '_dist'] = d
+        out[name + '_vol'] = vol_ref.astype(np.float32)     # values are float32 dists or -1/0/+1: exact
+        out[name + '_iters'] = iters
+        # a different (sigma, threshold) pair as well
+        v2 = ref_sdf.propagate_sign(vol_scatter.copy(), 3, 5)
+        v2o, _ = orc.propagate_sign(vol_scatter.copy(), 3, 5)
+        assert np.array_equal(v2, v2o)
+        out[name + '_vol_s3t5'] = v2.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, 'volume.npz'), **out)
+
+
+def gen_grid():
+    out = {}
+    for name, kind, n, res, eps in (('sphere64e3', 'sphere', 10000, 64, 3), ('torus48e4', 'torus', 4000, 48, 4),
+                                    ('box40e2', 'box', 3000, 40, 2), ('sphere32e5', 'sphere', 2000, 32, 5)):
+        cloud = synth.make_cloud(kind, n, seed=2)
+        q = ref_sdf.get_voxel_centers_grid_smaller_pc(cloud, res, eps)
+        idx = orc.query_grid_indices(cloud, res, eps)
+        assert np.array_equal(orc.volume_space_to_model_space(idx, res).astype(np.float32), q)
+        assert np.array_equal(idx, orc.query_grid_indices_shifts(cloud, res, eps)), name
+        out[name + '_count'] = len(q)
+        out[name + '_idxsum'] = idx.astype(np.int64).sum(axis=0)
+        out[name + '_lin_xor'] = np.bitwise_xor.reduce((idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2])
+        out[name + '_first'] = q[:4]
+        out[name + '_last'] = q[-4:]
+        print('grid', name, len(q))
+    np.savez_compressed(os.path.join(HERE, 'grid.npz'), **out)
+
+
+if __name__ == '__main__':
+    gen_grid()
+    gen_volume()
+    gen_assembly()
+    gen_model()
+    print('golden fixtures written to', HERE)
