@@ -1,0 +1,355 @@
+// K2 / K3: per-query patch assembly -- PointcloudPatchDataset.__getitem__ (source/data_loader.py:322-421).
+//   K2  exact kNN (k smallest float64 distances on float32 coordinates, i.e. scipy cKDTree semantics,
+//       source/base/point_cloud.py:174-175), patch radius and patch-space normalisation in float32
+//       exactly like NumPy (source/base/utils.py:62-69,80-88).
+//   K3  global sub-sample (source/base/utils.py:196-227): uniform with replacement, or distance-weighted
+//       without replacement via exponential clocks (Efraimidis-Spirakis), which realises the same
+//       successive-sampling law as RandomState.choice(replace=False, p).
+// One CTA per query; the cloud (N*12 B, L1/L2-resident) is streamed twice per selection:
+// a histogram pass over the top bits of the (monotone) key, then a collect pass.  All byte/compare work.
+#include "common.cuh"
+
+namespace p2s {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBins = 2048;
+constexpr int kCap = 1024;  // boundary-bin candidates that are sorted exactly
+
+// ---- key helpers: non-negative doubles order like their bit patterns ----
+__device__ __forceinline__ unsigned long long dkey(double v) { return (unsigned long long)__double_as_longlong(v); }
+// level-0 bin: sign+exponent+4 mantissa bits, rebased so that 2^-100 .. 2^27 maps to 0..2047
+__device__ __forceinline__ int bin0(unsigned long long key) {
+    long long b = (long long)(key >> 48) - ((1023 - 100) << 4);
+    return (int)(b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b));
+}
+
+struct SelectSmem {
+    unsigned hist[kBins];
+    unsigned long long cand_key[kCap];
+    int cand_id[kCap];
+    int bin_sel[4];       // selected bin per level
+    unsigned below;       // number of keys strictly below the boundary bin
+    unsigned n_direct;    // slots used by "surely in" members
+    unsigned n_cand;      // boundary candidates collected
+    int levels;           // refinement levels used (1..3)
+};
+
+// does `key` fall in the boundary bin chain selected so far (levels [0, upto))?
+__device__ __forceinline__ int chain_cmp(const SelectSmem& s, unsigned long long key, int upto) {
+    // returns -1 if key sorts below the chain, 0 if inside, +1 above
+    int b = bin0(key);
+    if (b != s.bin_sel[0]) return b < s.bin_sel[0] ? -1 : 1;
+    for (int l = 1; l < upto; ++l) {
+        int bl = (int)((key >> (48 - 11 * l)) & 0x7FF);
+        if (bl != s.bin_sel[l]) return bl < s.bin_sel[l] ? -1 : 1;
+    }
+    return 0;
+}
+
+// Block-wide: find the bin chain that contains the k-th smallest key.  KeyFn(i) -> key of item i.
+template <class KeyFn>
+__device__ void find_boundary(SelectSmem& s, int N, int k, int cand_cap, KeyFn keyfn) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { s.below = 0; s.levels = 0; }
+    for (int level = 0; level < 3; ++level) {
+        for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += kThreads) {
+            unsigned long long key = keyfn(i);
+            if (level == 0) atomicAdd(&s.hist[bin0(key)], 1u);
+            else if (chain_cmp(s, key, level) == 0) atomicAdd(&s.hist[(int)((key >> (48 - 11 * level)) & 0x7FF)], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {  // warp 0: locate the bin where the running count crosses k
+            unsigned need = (unsigned)k - s.below;  // rank inside the current chain, 1-based
+            unsigned run = 0;
+            int found = -1;
+            unsigned below_add = 0;
+            for (int base = 0; base < kBins && found < 0; base += 32) {
+                unsigned c = s.hist[base + tid];
+                unsigned incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                unsigned excl = incl - c;
+                unsigned hit = __ballot_sync(0xffffffffu, run + incl >= need);
+                if (hit) {
+                    int lane = __ffs(hit) - 1;
+                    found = base + lane;
+                    below_add = run + __shfl_sync(0xffffffffu, excl, lane);
+                }
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) {
+                s.bin_sel[level] = found;
+                s.below += below_add;
+                s.levels = level + 1;
+            }
+        }
+        __syncthreads();
+        if (s.hist[s.bin_sel[level]] <= (unsigned)cand_cap) break;  // uniform: same smem value for all threads
+        __syncthreads();
+    }
+}
+
+// bitonic sort of (key, id) ascending over kCap slots (slots >= n are padded with +inf keys)
+__device__ void sort_candidates(SelectSmem& s, int n) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kCap; i += kThreads)
+        if (i >= n) { s.cand_key[i] = ~0ull; s.cand_id[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int size = 2; size <= kCap; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < kCap / 2; t += kThreads) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                unsigned long long ka = s.cand_key[lo], kb = s.cand_key[hi];
+                int ia = s.cand_id[lo], ib = s.cand_id[hi];
+                bool gt = (ka > kb) || (ka == kb && ia > ib);
+                if (gt == up) { s.cand_key[lo] = kb; s.cand_key[hi] = ka; s.cand_id[lo] = ib; s.cand_id[hi] = ia; }
+            }
+            __syncthreads();
+        }
+}
+
+__device__ __forceinline__ double dist2_f64(const float* __restrict__ pts, int i, double qx, double qy, double qz) {
+    // cKDTree: sum over dimensions of (x-y)^2, float64, sequential, no FMA contraction
+    double dx = (double)pts[i * 3 + 0] - qx, dy = (double)pts[i * 3 + 1] - qy, dz = (double)pts[i * 3 + 2] - qz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// NumPy float32: np.linalg.norm(q - p) = sqrt((dx*dx + dy*dy) + dz*dz), every op rounded to float32
+__device__ __forceinline__ float norm_f32(float dx, float dy, float dz) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int k,
+                 int32_t* __restrict__ ids_out, float* __restrict__ patch_out, float* __restrict__ radius_out,
+                 int* __restrict__ err_flag) {
+    __shared__ SelectSmem s;
+    __shared__ float red[kThreads / 32];
+    __shared__ float s_radius;
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const float qxf = queries[q * 3 + 0], qyf = queries[q * 3 + 1], qzf = queries[q * 3 + 2];
+    const double qx = qxf, qy = qyf, qz = qzf;
+    auto keyfn = [&](int i) { return dkey(dist2_f64(pts, i, qx, qy, qz)); };
+
+    find_boundary(s, N, k, kCap - 512, keyfn);
+    if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
+    __syncthreads();
+    const int levels = s.levels;
+    // collect: keys below the boundary chain are members; keys inside it are candidates
+    for (int i = tid; i < N; i += kThreads) {
+        unsigned long long key = keyfn(i);
+        int c = chain_cmp(s, key, levels);
+        if (c < 0) {
+            // members go to the tail of the candidate arrays so one sort orders everything
+            unsigned slot = atomicAdd(&s.n_direct, 1u);
+            if (slot < (unsigned)kCap) { s.cand_key[kCap - 1 - slot] = key; s.cand_id[kCap - 1 - slot] = i; }
+        } else if (c == 0) {
+            unsigned slot = atomicAdd(&s.n_cand, 1u);
+            if (slot < (unsigned)kCap) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+        }
+    }
+    __syncthreads();
+    const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
+    if (n_direct + n_cand > (unsigned)kCap || n_direct != s.below) {
+        // more than kCap points tie into the boundary bin even after 3 refinement levels (degenerate cloud)
+        if (tid == 0) atomicExch(err_flag, 1);
+        return;
+    }
+    // compact: move the members right behind the candidates, then sort everything exactly
+    __syncthreads();
+    unsigned long long mk[(kCap + kThreads - 1) / kThreads];
+    int mi[(kCap + kThreads - 1) / kThreads];
+    int cnt = 0;
+    for (unsigned j = tid; j < n_direct; j += kThreads) { mk[cnt] = s.cand_key[kCap - 1 - j]; mi[cnt] = s.cand_id[kCap - 1 - j]; ++cnt; }
+    __syncthreads();
+    cnt = 0;
+    for (unsigned j = tid; j < n_direct; j += kThreads) { s.cand_key[n_cand + j] = mk[cnt]; s.cand_id[n_cand + j] = mi[cnt]; ++cnt; }
+    __syncthreads();
+    sort_candidates(s, (int)(n_direct + n_cand));
+
+    // radius = max float32 norm over the k neighbours (utils.get_patch_radii)
+    float r = 0.f;
+    for (int j = tid; j < k; j += kThreads) {
+        int id = s.cand_id[j];
+        r = fmaxf(r, norm_f32(__fsub_rn(qxf, pts[id * 3 + 0]), __fsub_rn(qyf, pts[id * 3 + 1]), __fsub_rn(qzf, pts[id * 3 + 2])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((tid & 31) == 0) red[tid >> 5] = r;
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0];
+        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[w]);
+        s_radius = m;
+        radius_out[q] = m;
+    }
+    __syncthreads();
+    const float radius = s_radius;
+    for (int j = tid; j < k; j += kThreads) {
+        int id = s.cand_id[j];
+        if (ids_out) ids_out[q * k + j] = id;
+        float* o = patch_out + (q * k + j) * 3;
+        // model_space_to_patch_space: (p - q) / r in float32
+        o[0] = __fdiv_rn(__fsub_rn(pts[id * 3 + 0], qxf), radius);
+        o[1] = __fdiv_rn(__fsub_rn(pts[id * 3 + 1], qyf), radius);
+        o[2] = __fdiv_rn(__fsub_rn(pts[id * 3 + 2], qzf), radius);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1]
+    return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, int S, uint64_t seed, int32_t* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int quads = (S + 3) / 4;
+    if (t >= Q * quads) return;
+    int64_t q = t / quads;
+    int j4 = (int)(t % quads);
+    uint32_t r[4];
+    uint64_t qi = (uint64_t)(qbase + q);
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)j4, 0x5ab5a3e1u, r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int j = j4 * 4 + e;
+        if (j < S) out[q * S + j] = (int32_t)(((uint64_t)r[e] * (uint64_t)N) >> 32);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries,
+                          int64_t qbase, int S, uint64_t seed, int32_t* __restrict__ out, int* __restrict__ err_flag) {
+    __shared__ SelectSmem s;
+    __shared__ float red[kThreads / 32];
+    __shared__ float s_dmax;
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const float qx = queries[q * 3 + 0], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
+    // dist_prob (utils.py:200-208): float32 like NumPy
+    float dmax = 0.f;
+    for (int i = tid; i < N; i += kThreads)
+        dmax = fmaxf(dmax, norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = dmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0];
+        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[w]);
+        s_dmax = m;
+    }
+    __syncthreads();
+    dmax = s_dmax;
+    const uint64_t qi = (uint64_t)(qbase + q);
+    auto keyfn = [&](int i) {
+        float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
+        float dn = __fdiv_rn(d, dmax);
+        float w = __fsub_rn(1.0f, __fmul_rn(1.5f, dn));
+        w = fminf(fmaxf(w, 0.05f), 1.0f);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)(i >> 2), 0x77f1e2d3u, r);
+        float u = u01_open(r[i & 3]);
+        // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
+        double e = (double)(-__logf(u)) / (double)w;
+        return dkey(e);
+    };
+    find_boundary(s, N, S, kCap, keyfn);
+    if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
+    __syncthreads();
+    const int levels = s.levels;
+    for (int i = tid; i < N; i += kThreads) {
+        unsigned long long key = keyfn(i);
+        int c = chain_cmp(s, key, levels);
+        if (c < 0) {
+            unsigned slot = atomicAdd(&s.n_direct, 1u);
+            if (slot < (unsigned)S) out[q * S + slot] = i;
+        } else if (c == 0) {
+            unsigned slot = atomicAdd(&s.n_cand, 1u);
+            if (slot < (unsigned)kCap) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+        }
+    }
+    __syncthreads();
+    const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
+    if (n_cand > (unsigned)kCap || n_direct != s.below || n_direct + n_cand < (unsigned)S) {
+        if (tid == 0) atomicExch(err_flag, 2);
+        return;
+    }
+    sort_candidates(s, (int)n_cand);
+    for (unsigned j = tid; n_direct + j < (unsigned)S; j += kThreads) out[q * S + n_direct + j] = s.cand_id[j];
+}
+
+__global__ void gather_points_kernel(const float* __restrict__ pts, const int32_t* __restrict__ ids, int64_t count, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int id = ids[i];
+    out[i * 3 + 0] = pts[id * 3 + 0];
+    out[i * 3 + 1] = pts[id * 3 + 1];
+    out[i * 3 + 2] = pts[id * 3 + 2];
+}
+
+}  // namespace
+
+static int* err_flag_dev() {
+    static thread_local int* flag = nullptr;
+    if (!flag) {
+        P2S_CUDA(cudaMalloc(&flag, sizeof(int)));
+        P2S_CUDA(cudaMemset(flag, 0, sizeof(int)));
+    }
+    return flag;
+}
+
+int assemble_error_check(cudaStream_t st) {  // sync; returns and clears the device error flag
+    int h = 0;
+    int* f = err_flag_dev();
+    P2S_CUDA(cudaMemcpyAsync(&h, f, sizeof(int), cudaMemcpyDeviceToHost, st));
+    P2S_CUDA(cudaStreamSynchronize(st));
+    if (h) P2S_CUDA(cudaMemsetAsync(f, 0, sizeof(int), st));
+    return h;
+}
+
+void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids,
+               float* patch, float* radius, cudaStream_t st) {
+    P2S_CHECK(N >= k, "kNN needs N >= k (the reference returns out-of-range ids otherwise)");
+    P2S_CHECK(k >= 1 && k <= 512, "k must be in [1, 512]");
+    P2S_CHECK(N < (1 << 30), "cloud too large");
+    if (Q <= 0) return;
+    P2S_LAUNCH(knn_patch_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, k, ids, patch, radius, err_flag_dev());
+}
+
+void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S,
+               int mode, uint64_t seed, int32_t* out, cudaStream_t st) {
+    P2S_CHECK(N >= S, "sub-sample needs N >= sub_sample_size (reference zero-pads after an in-place shuffle; unsupported)");
+    P2S_CHECK(N < (1 << 30), "cloud too large");
+    if (Q <= 0) return;
+    if (mode == P2S_SUBSAMPLE_UNIFORM) {
+        int64_t threads = Q * ((S + 3) / 4);
+        P2S_LAUNCH(subsample_uniform_kernel, (unsigned)cdiv(threads, 256), 256, 0, st, (int)N, Q, qbase, S, seed, out);
+    } else if (mode == P2S_SUBSAMPLE_WEIGHTED) {
+        P2S_LAUNCH(subsample_weighted_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+    } else {
+        throw Error("unknown sub-sample mode");
+    }
+}
+
+void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st) {
+    if (count <= 0) return;
+    P2S_LAUNCH(gather_points_kernel, (unsigned)cdiv(count, 256), 256, 0, st, pts, ids, count, out);
+}
+
+}  // namespace p2s

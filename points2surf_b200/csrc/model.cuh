@@ -1,0 +1,72 @@
+// Device-resident model: folded fp32 weights (accuracy path) + packed fp16 operand tiles (tensor-core path).
+#pragma once
+#include "common.cuh"
+
+namespace p2s {
+
+struct Layer {
+    const float* W = nullptr;  // [cout][cin] row-major, BN folded
+    const float* b = nullptr;  // [cout]
+    int cout = 0, cin = 0;
+};
+
+struct Stn {  // QSTN (out 4) or STN dim 64 (out 4096): source/points_to_surf_model.py:12-131
+    Layer c1, c2, c3, fc1, fc2, fc3;
+};
+
+struct Feat {  // PointNetfeat: source/points_to_surf_model.py:134-234
+    bool has_qstn = false;
+    Stn stn1, stn2;
+    Layer conv0a, conv0b, conv1, conv2, conv3;
+};
+
+struct TcWeights;  // net_tc.cu
+
+struct Model {
+    p2s_model_config cfg{};
+    int device = 0;
+    float* blob = nullptr;  // device copy of the folded fp32 blob
+    size_t blob_floats = 0;
+    bool shared_qstn = false;
+    Stn point_stn;
+    Feat local, global;
+    Layer fc1_local, fc1_global, fc2, fc3, fc4;
+
+    int precision = P2S_PRECISION_FP32;
+    float guard_band = 0.f;
+    TcWeights* tc = nullptr;
+
+    cudaStream_t own_stream = nullptr;  // used by the *_host entry points
+    DevBuf ws_net;                       // network activations
+    DevBuf ws_io;                        // staged host inputs / assembled query batches
+    DevBuf ws_misc;
+    DevBuf ws_guard;
+    DevBuf ws_host;                      // device staging of host-call inputs/outputs
+    int64_t* guard_count_dev = nullptr;
+    int64_t last_guard_count = 0;
+};
+
+// net_fp32.cu
+void forward_fp32(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+                  float* logits, cudaStream_t st);
+// net_tc.cu
+void tc_build(Model& m);
+void tc_destroy(Model& m);
+void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+                float* logits, cudaStream_t st);
+// dispatch (api.cu)
+void forward(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+             float* logits, cudaStream_t st);
+
+// small shared kernels (net_fp32.cu), also used by the TC path for the per-query FC tails
+void launch_gemm_nt(const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z,
+                    const float* bias, float* C, int64_t c_stride_z, int ldc, int M, int N, int K,
+                    int batch, bool relu, cudaStream_t st);
+void launch_gemm_nt_colmax(const float* A, int64_t a_stride_z, int lda, const float* W, float* out,
+                           int M, int N, int K, int batch, cudaStream_t st);
+void launch_fill(float* p, int64_t n, float v, cudaStream_t st);
+void launch_bias_act(float* x, const float* bias, int64_t rows, int cols, bool relu, cudaStream_t st);
+void launch_quat_to_rot(const float* q4, float* R, int64_t B, cudaStream_t st);
+void launch_add_identity64(float* T, int64_t B, cudaStream_t st);
+
+}  // namespace p2s

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/p2s_b200.h declares; the Python
+binding declares a prototype for each; host-only helpers behave; there is no CPU compute path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from points2surf_b200 import _lib, weights, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'p2s_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(p2s_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), 'missing export: ' + s
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.p2s_abi_version() == 1
+
+
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_blob_size_matches_library(variant):
+    lib = _lib.load()
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict_numpy(variant, 0, module_prefix='module.')
+    blob = weights.pack_blob(sd, v['use_point_stn'], v['shared_transformer'])
+    cfg = _lib.ModelConfig(v['use_point_stn'], v['shared_transformer'], 300, 1000, 1024)
+    assert blob.size == lib.p2s_model_blob_floats(C.byref(cfg))
+    assert blob.dtype == np.float32 and np.isfinite(blob).all()
+
+
+def test_bn_folding_matches_batchnorm():
+    import torch
+    import torch.nn.functional as F
+    sd = synth.make_state_dict('max', 1)
+    w, b = weights.fold(sd, 'feat_local.conv2', 'feat_local.bn2')
+    x = torch.randn(5, 64, 7)
+    y = F.batch_norm(F.conv1d(x, sd['feat_local.conv2.weight'], sd['feat_local.conv2.bias']),
+                     sd['feat_local.bn2.running_mean'], sd['feat_local.bn2.running_var'],
+                     sd['feat_local.bn2.weight'], sd['feat_local.bn2.bias'], False, 0.0, 1e-5)
+    y2 = F.conv1d(x, torch.from_numpy(w.reshape(128, 64, 1)), torch.from_numpy(b))
+    assert torch.allclose(y, y2, atol=1e-4)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from points2surf_b200 import ops
+    with pytest.raises(_lib.P2SError):
+        ops.Engine(synth.make_state_dict('max', 0), 0, 0)
+    with pytest.raises(_lib.P2SError):
+        ops.query_grid(torch.zeros(10, 3), 16, 3)

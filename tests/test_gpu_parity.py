@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (points2surf_b200.ops -> ctypes ->
+libp2s_b200.so), against the oracle and the committed golden vectors.
+Integer / index work must be bit-exact; floating point tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2s_oracle as orc
+from points2surf_b200 import synth, ops
+from helpers import load_golden, golden_model_case, calibrated_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def make_engine(sd, variant, **kw):
+    v = synth.VARIANTS[variant]
+    return ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], **kw)
+
+
+# ------------------------------------------------------------------ a7 / a8 : network
+# fp32 path tolerance: |logit error| <= 2e-3 absolute on logits of magnitude O(1..30) (fp32 FMA with a
+# different summation order than the CPU BLAS); sign class must be identical on the golden batch.
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_forward_fp32_matches_golden(variant):
+    sd, inp, g = golden_model_case(variant)
+    eng = make_engine(sd, variant)
+    out = eng.forward(cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms'])).cpu().numpy()
+    err = np.abs(out - g['logits']).max()
+    assert err < 2e-3, err
+    assert ((out[:, 1] >= 0) == (g['logits'][:, 1] >= 0)).all()
+    # host-buffer entry point gives the same bits as the device entry point
+    out_h = eng.forward_host(inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'])
+    assert np.array_equal(out, out_h)
+    sdf = ops.sdf_from_logits(cu(g['logits']), cu(g['radius'])).cpu().numpy()
+    np.testing.assert_allclose(sdf, g['sdf'], rtol=2e-6, atol=1e-8)
+    assert np.array_equal(np.sign(sdf), np.sign(g['sdf']))
+
+
+def test_forward_fp32_ragged_batch_and_no_mutation():
+    # batch sizes around the internal chunking (256) and a batch of 1; inputs must not be modified
+    sd = calibrated_state_dict('vanilla', 21)
+    eng = make_engine(sd, 'vanilla')
+    inp = synth.make_model_inputs(300, seed=5)
+    pa, su, qu = cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms'])
+    su_before = su.clone()
+    full = eng.forward(pa, su, qu)
+    assert torch.equal(su, su_before)
+    one = eng.forward(pa[257:258], su[257:258], qu[257:258])
+    assert torch.allclose(full[257:258], one, atol=1e-4)
+    ref = orc.model_forward(sd, inp['patch_pts_ps'][250:262], inp['pts_sub_sample_ms'][250:262],
+                            inp['imp_surf_query_point_ms'][250:262], 1, 1)
+    assert np.abs(full[250:262].cpu().numpy() - ref).max() < 2e-3
+    assert eng.forward(pa[:0], su[:0], qu[:0]).shape == (0, 2)
+
+
+def test_nan_logit_becomes_one():
+    lg = cu(np.array([[np.nan, 1.0], [0.5, -1.0]], np.float32))
+    sdf = ops.sdf_from_logits(lg, cu(np.array([0.1, 0.2], np.float32))).cpu().numpy()
+    assert sdf[0] == 1.0 and sdf[1] < 0
+
+
+# ------------------------------------------------------------------ a1 : candidate grid (bit-exact)
+@pytest.mark.parametrize('kind,n,res,eps', [('sphere', 10000, 64, 3), ('torus', 4000, 48, 4), ('box', 3000, 40, 2),
+                                            ('sphere', 2000, 32, 5), ('sphere', 300, 16, 1), ('box', 5000, 127, 3)])
+def test_query_grid_bit_exact(kind, n, res, eps):
+    cloud = synth.make_cloud(kind, n, seed=2)
+    lin = ops.query_grid(cu(cloud), res, eps)
+    idx = orc.query_grid_indices(cloud, res, eps)
+    ref_lin = (idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2]
+    assert np.array_equal(lin.cpu().numpy().astype(np.int64), ref_lin)
+    q = ops.query_points(lin, res).cpu().numpy()
+    assert np.array_equal(q, orc.query_grid(cloud, res, eps))
+
+
+def test_query_grid_golden_counts():
+    g = load_golden('grid.npz')
+    for name, kind, n, res, eps in (('sphere64e3', 'sphere', 10000, 64, 3), ('torus48e4', 'torus', 4000, 48, 4)):
+        lin = ops.query_grid(cu(synth.make_cloud(kind, n, seed=2)), res, eps).cpu().numpy().astype(np.int64)
+        assert len(lin) == int(g[name + '_count'])
+        assert np.bitwise_xor.reduce(lin) == int(g[name + '_lin_xor'])
+
+
+def test_query_grid_points_outside_cube_are_ignored():
+    cloud = synth.make_cloud('sphere', 1000, seed=3)
+    bad = np.concatenate([cloud, np.array([[1.5, 0, 0], [0, -1.2, 0], [0, 0, 1.0]], np.float32)])
+    a = ops.query_grid(cu(cloud), 32, 3).cpu().numpy()
+    b = ops.query_grid(cu(bad), 32, 3).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ a4 / a5 : kNN patch (bit-exact)
+def test_knn_patch_golden():
+    g = load_golden('assembly.npz')
+    cloud, res, k = g['cloud'], int(g['res']), int(g['k'])
+    qpts = orc.volume_space_to_model_space(g['query_idx'].astype(np.int64), res).astype(np.float32)
+    ids, patch, radius = ops.knn_patch(cu(cloud), cu(qpts[:6]), k)
+    assert np.array_equal(ids.cpu().numpy(), g['patch_ids'])          # same order as cKDTree (ascending distance)
+    assert np.array_equal(radius.cpu().numpy(), g['radius'])
+    assert np.array_equal(patch.cpu().numpy(), g['patch_ps'])
+
+
+def test_knn_patch_vs_oracle_many_queries():
+    cloud = synth.make_cloud('torus', 7000, seed=4)
+    qpts = orc.query_grid(cloud, 32, 3)
+    sel = np.random.RandomState(0).choice(len(qpts), 400, replace=False)
+    q = qpts[sel]
+    ids, patch, radius = ops.knn_patch(cu(cloud), cu(q), 300)
+    ids, patch, radius = ids.cpu().numpy(), patch.cpu().numpy(), radius.cpu().numpy()
+    kd = orc.make_kdtree(cloud)
+    for i in range(len(q)):
+        oid, ops_, orad = orc.knn_patch(cloud, kd, q[i], 300)
+        _, d2 = orc.knn_bruteforce(cloud, q[i], 300)
+        assert set(ids[i].tolist()) == set(oid.tolist())
+        gd = ((cloud[ids[i]].astype(np.float64) - q[i].astype(np.float64)) ** 2).sum(1)
+        assert np.array_equal(gd, d2)                   # ascending, identical float64 distances
+        assert radius[i] == orad
+        if np.all(np.diff(d2) > 0):                      # no exact ties -> order is unique
+            assert np.array_equal(ids[i], oid)
+            assert np.array_equal(patch[i], ops_)
+
+
+def test_knn_small_k_and_duplicates():
+    rng = np.random.RandomState(1)
+    cloud = rng.uniform(-0.9, 0.9, (500, 3)).astype(np.float32)
+    cloud[100:110] = cloud[100]                          # exact duplicates -> ties
+    q = cloud[100:101] + np.float32(0.01)
+    ids, patch, radius = ops.knn_patch(cu(cloud), cu(q), 8)
+    bid, d2 = orc.knn_bruteforce(cloud, q[0], 8)
+    gd = ((cloud[ids[0].cpu().numpy()].astype(np.float64) - q[0].astype(np.float64)) ** 2).sum(1)
+    assert np.array_equal(gd, d2)
+    with pytest.raises(ops.P2SError):
+        ops.knn_patch(cu(cloud[:5]), cu(q), 8)           # N < k: the reference would index out of range
+
+
+# ------------------------------------------------------------------ a6 : sub-sample
+def test_subsample_uniform_properties():
+    cloud = synth.make_cloud('sphere', 5000, seed=1)
+    q = cu(orc.query_grid(cloud, 16, 3)[:64])
+    a = ops.subsample(cu(cloud), q, 1000, True, seed=7).cpu().numpy()
+    assert a.shape == (64, 1000) and a.min() >= 0 and a.max() < 5000
+    # counter-based: independent of how the query list is split
+    b = ops.subsample(cu(cloud), q[10:20], 1000, True, seed=7, query_index_base=10).cpu().numpy()
+    assert np.array_equal(a[10:20], b)
+    assert not np.array_equal(a, ops.subsample(cu(cloud), q, 1000, True, seed=8).cpu().numpy())
+    # uniform over ids: chi-square-ish bound on bucket counts (64000 draws over 50 buckets)
+    cnt = np.bincount(a.ravel() // 100, minlength=50)
+    assert abs(cnt - 1280).max() < 6 * np.sqrt(1280)
+
+
+def test_subsample_weighted_is_without_replacement_and_matches_reference_law():
+    # inclusion frequencies of the GPU sampler vs RandomState.choice(replace=False, p) on a small cloud
+    rng = np.random.RandomState(3)
+    cloud = rng.uniform(-0.9, 0.9, (40, 3)).astype(np.float32)
+    qp = np.array([[0.3, -0.2, 0.1]], np.float32)
+    trials = 4000
+    q = cu(np.repeat(qp, trials, axis=0))
+    ids = ops.subsample(cu(cloud), q, 10, False, seed=11).cpu().numpy()
+    assert all(len(set(r.tolist())) == 10 for r in ids)
+    freq_gpu = np.bincount(ids.ravel(), minlength=40) / trials
+    prob = orc.sub_sample_probabilities(cloud, qp[0])
+    rs = np.random.RandomState(5)
+    ref = np.stack([rs.choice(40, size=10, replace=False, p=prob) for _ in range(trials)])
+    freq_ref = np.bincount(ref.ravel(), minlength=40) / trials
+    # binomial std of an inclusion frequency ~ sqrt(.25*.75/4000) = 0.007; two estimates -> 5 sigma = 0.05
+    assert np.abs(freq_gpu - freq_ref).max() < 0.05, np.abs(freq_gpu - freq_ref).max()
+    # and the law is really non-uniform (near points favoured)
+    near = np.argsort(np.linalg.norm(cloud - qp[0], axis=1))
+    assert freq_gpu[near[:10]].mean() > freq_gpu[near[-10:]].mean() + 0.1
+
+
+def test_subsample_requires_enough_points():
+    cloud = synth.make_cloud('sphere', 100, seed=1)
+    with pytest.raises(ops.P2SError):
+        ops.subsample(cu(cloud), cu(cloud[:2]), 1000, True, seed=1)
+
+
+# ------------------------------------------------------------------ a10 / a11 : volume (bit-exact)
+@pytest.mark.parametrize('name', ['sphere', 'noisy'])
+def test_sign_propagation_golden(name):
+    g = load_golden('volume.npz')
+    res = int(g[name + '_res'])
+    idx = orc.model_space_to_volume_space(g[name + '_qpts'], res)
+    lin = ((idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2]).astype(np.int32)
+    vol, iters = ops.sdf_to_volume(cu(lin), cu(g[name + '_dist']), res, 5, 13.0)
+    ref = np.clip(g[name + '_vol'], -1.0, 1.0)
+    assert np.array_equal(vol.cpu().numpy(), ref)
+    assert iters == int(g[name + '_iters'])
+    vol2, _ = ops.sdf_to_volume(cu(lin), cu(g[name + '_dist']), res, 3, 5.0)
+    assert np.array_equal(vol2.cpu().numpy(), np.clip(g[name + '_vol_s3t5'], -1.0, 1.0))
+
+
+@pytest.mark.parametrize('res,sigma,thr', [(24, 5, 13), (33, 4, 9), (48, 5, 26), (20, 2, 3)])
+def test_sign_propagation_vs_oracle(res, sigma, thr):
+    cloud = synth.make_cloud('torus', 4000, seed=9)
+    qpts = orc.query_grid(cloud, res, 3)
+    rng = np.random.RandomState(res)
+    d = (rng.standard_normal(len(qpts)) * 0.05).astype(np.float32)
+    d[np.linalg.norm(qpts, axis=1) < 0.4] *= np.sign(d[np.linalg.norm(qpts, axis=1) < 0.4])   # mostly + inside
+    ref = orc.sdf_to_volume(d, qpts, res, sigma, thr)
+    idx = orc.model_space_to_volume_space(qpts, res)
+    lin = ((idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2]).astype(np.int32)
+    vol, _ = ops.sdf_to_volume(cu(lin), cu(d), res, sigma, float(thr))
+    assert np.array_equal(vol.cpu().numpy().astype(np.float64), ref)
+
+
+def test_all_zero_band_is_reported():
+    lin = cu(np.arange(10, dtype=np.int32))
+    vol, iters = ops.sdf_to_volume(lin, cu(np.zeros(10, np.float32)), 8, 5, 13.0)
+    assert iters == -1
+
+
+# ------------------------------------------------------------------ fused pipeline
+@pytest.mark.parametrize('variant', ['vanilla', 'max'])
+def test_reconstruct_matches_stagewise_oracle(variant):
+    v = synth.VARIANTS[variant]
+    sd = calibrated_state_dict(variant, 31)
+    eng = make_engine(sd, variant)
+    cloud = synth.make_cloud('sphere', 3000, seed=6)
+    res, eps, seed = 16, 3, 1234
+    lin, sdf = eng.reconstruct(cu(cloud), res, eps, v['uniform_subsample'], seed)
+    idx = orc.query_grid_indices(cloud, res, eps)
+    assert np.array_equal(lin.cpu().numpy().astype(np.int64), (idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2])
+    # replay a few queries on the CPU with the GPU's own sub-sample ids (RNG streams differ by design)
+    qpts = orc.query_grid(cloud, res, eps)
+    sel = [0, 1, len(qpts) // 2, len(qpts) - 1]
+    sub_ids = ops.subsample(cu(cloud), cu(qpts), 1000, bool(v['uniform_subsample']), seed).cpu().numpy()
+    kd = orc.make_kdtree(cloud)
+    patches, radii = zip(*[(orc.knn_patch(cloud, kd, qpts[i], 300)[1:]) for i in sel])
+    logits = orc.model_forward(sd, np.stack(patches), cloud[sub_ids[sel]], qpts[sel], v['use_point_stn'], v['shared_transformer'])
+    ref = orc.post_process(logits, np.array(radii))
+    got = sdf.cpu().numpy()[sel]
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4)
+    # slab sharding (multi-GPU tile mode) reproduces the same numbers
+    lin2, sdf2 = eng.reconstruct(cu(cloud), res, eps, v['uniform_subsample'], seed, first_query=100, num_queries=50)
+    assert torch.equal(lin2, lin[100:150]) and torch.allclose(sdf2, sdf[100:150], atol=1e-6)
+    # host entry point
+    lin3, sdf3 = eng.reconstruct_host(cloud, res, eps, v['uniform_subsample'], seed, cap=len(qpts))
+    assert np.array_equal(lin3, lin.cpu().numpy()) and np.allclose(sdf3, sdf.cpu().numpy(), atol=1e-6)

@@ -1,0 +1,77 @@
+"""CPU: the oracle restatement against the golden vectors generated from the real reference
+(tests/golden/make_golden.py).  Keeps the oracle pinned on boxes where /root/reference is absent."""
+import numpy as np
+import pytest
+
+from oracle import p2s_oracle as orc
+from points2surf_b200 import synth
+from helpers import load_golden, golden_model_case
+
+
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_model_forward_matches_reference(variant):
+    sd, inp, g = golden_model_case(variant)
+    v = synth.VARIANTS[variant]
+    out, aux = orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'],
+                                 v['use_point_stn'], v['shared_transformer'], return_aux=True)
+    np.testing.assert_allclose(out, g['logits'], rtol=0, atol=2e-4)   # fp32 CPU, different BLAS threads/blocking
+    np.testing.assert_allclose(aux['feat_global_max'][:2], g['feat_global_max'], rtol=1e-4, atol=1e-4)
+    assert ((out[:, 1] >= 0) == (g['logits'][:, 1] >= 0)).all()
+    np.testing.assert_allclose(orc.post_process(g['logits'], g['radius']), g['sdf'], rtol=1e-6, atol=1e-7)
+    assert 0 < (g['logits'][:, 1] >= 0).sum() < 8   # mixed sign classes: the test is not vacuous
+
+
+def test_forward_does_not_mutate_inputs():
+    sd, inp, g = golden_model_case('vanilla')
+    before = inp['pts_sub_sample_ms'].copy()
+    orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'], 1, 1)
+    assert np.array_equal(before, inp['pts_sub_sample_ms'])
+
+
+def test_query_grid_golden():
+    g = load_golden('grid.npz')
+    for name, kind, n, res, eps in (('sphere64e3', 'sphere', 10000, 64, 3), ('torus48e4', 'torus', 4000, 48, 4),
+                                    ('box40e2', 'box', 3000, 40, 2), ('sphere32e5', 'sphere', 2000, 32, 5)):
+        cloud = synth.make_cloud(kind, n, seed=2)
+        idx = orc.query_grid_indices(cloud, res, eps)
+        assert len(idx) == int(g[name + '_count'])
+        assert np.array_equal(idx.astype(np.int64).sum(axis=0), g[name + '_idxsum'])
+        assert np.array_equal(idx, orc.query_grid_indices_shifts(cloud, res, eps))
+        q = orc.query_grid(cloud, res, eps)
+        assert np.array_equal(q[:4], g[name + '_first']) and np.array_equal(q[-4:], g[name + '_last'])
+
+
+def test_assembly_golden():
+    g = load_golden('assembly.npz')
+    cloud, res, eps, k, S, seed = g['cloud'], int(g['res']), int(g['eps']), int(g['k']), int(g['S']), int(g['seed'])
+    idx = orc.query_grid_indices(cloud, res, eps)
+    assert np.array_equal(idx, g['query_idx'].astype(np.int64))
+    qpts = orc.volume_space_to_model_space(idx, res).astype(np.float32)
+    kd = orc.make_kdtree(cloud)
+    for uniform, tag in ((0, 'wgt'), (1, 'uni')):
+        rng = np.random.RandomState(seed)
+        for qi in range(6):
+            item = orc.assemble_query(cloud, kd, qpts[qi], k, S, rng, bool(uniform))
+            assert np.array_equal(item['patch_pts_ps'], g['patch_ps'][qi])
+            assert item['patch_radius_ms'] == g['radius'][qi]
+            assert np.array_equal(item['sub_sample_ids'], g['sub_ids_' + tag][qi])
+            bid, _ = orc.knn_bruteforce(cloud, qpts[qi], k)
+            assert set(bid.tolist()) == set(g['patch_ids'][qi].tolist())
+
+
+def test_sign_propagation_golden():
+    g = load_golden('volume.npz')
+    for name in ('sphere', 'noisy'):
+        res = int(g[name + '_res'])
+        vol = orc.sdf_to_volume(g[name + '_dist'], g[name + '_qpts'], res, 5, 13)
+        ref = np.clip(g[name + '_vol'].astype(np.float64), -1.0, 1.0)
+        assert np.array_equal(vol, ref)
+        v2 = np.zeros((res,) * 3)
+        v2 = orc.add_samples_to_volume(v2, g[name + '_qpts'], g[name + '_dist'])
+        v2, _ = orc.propagate_sign(v2, 3, 5)
+        assert np.array_equal(v2.astype(np.float32), g[name + '_vol_s3t5'])
+
+
+def test_all_zero_distances_are_skipped():
+    q = orc.query_grid(synth.make_cloud('sphere', 500, seed=1), 16, 3)
+    assert orc.sdf_to_volume(np.zeros(len(q), np.float32), q, 16, 5, 13) is None
