@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- SDF queries/s of the Points2Surf reconstruction hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one shape: point cloud -> candidate grid -> per query
+(kNN-300 patch, 1000-point sub-sample, PointNet stacks, |SDF|+sign) -> SDF band of Q queries.
+Workload (config.workload): vanilla model (shared QSTN, distance-weighted sub-sample), one synthetic
+10k-point cloud per GPU, grid_res 256, epsilon 3 -- the model/cloud of BASELINE.json configs[1] at the
+grid resolution its `metric` is quoted on; with --gpus N every rank reconstructs its own shape (weak scaling,
+no data-path collective, like configs[2]).
+
+  value : whole-job queries/s, cloud already resident in HBM when the timed region starts (device entry point)
+  e2e   : the same metric through the host-buffer C-ABI call (p2s_reconstruct_host): pinned host cloud in,
+          SDF band + voxel indices out, copies inside the timed region
+  roofline     : the dominant kernel (tensor-core PointNet pass) against MEASURED_PEAKS.json
+  cpu_baseline : the oracle port of the reference's CPU path on a bounded sample of the same queries
+
+`--impl reference` times the reference's own CPU algorithm (oracle port: scipy cKDTree + NumPy sampling +
+torch-CPU network, all host threads) on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_QUERY = {'vanilla': 1.1407e9, 'max': 0.7768e9}   # SURVEY.md section 8(d), eval mode, BN folded, un-padded
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--model', default='vanilla', choices=['vanilla', 'max'])
+    ap.add_argument('--grid_res', type=int, default=256)
+    ap.add_argument('--epsilon', type=int, default=3)
+    ap.add_argument('--points', type=int, default=10000)
+    ap.add_argument('--precision', default='auto', choices=['auto', 'tc', 'fp32'])
+    ap.add_argument('--guard_band', type=float, default=None)
+    ap.add_argument('--cpu_sample', type=int, default=48, help='queries in the bounded CPU-baseline sample')
+    ap.add_argument('--seed', type=int, default=40938661)
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def make_workload(args, rank):
+    from points2surf_b200 import synth
+    kinds = ['sphere', 'torus', 'box']
+    cloud = synth.make_cloud(kinds[rank % 3], args.points, seed=rank)
+    sd = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4)
+    return cloud, sd
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU side: oracle port of the reference path (test infrastructure used as the timed CPU baseline)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None):
+    """queries/s of the reference algorithm on the host cores for `n_queries` queries of this workload."""
+    import torch
+    from oracle import p2s_oracle as orc
+    from points2surf_b200 import synth
+    v = synth.VARIANTS[args.model]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if fc4_bias is not None:
+        sd = dict(sd)
+        sd['fc4.bias'] = torch.from_numpy(np.asarray(fc4_bias, dtype=np.float32))
+    t0 = time.perf_counter()
+    qpts = orc.query_grid(cloud, args.grid_res, args.epsilon)
+    t_grid = time.perf_counter() - t0
+    Q = len(qpts)
+    sel = np.linspace(0, Q - 1, n_queries).astype(np.int64)
+    kd = orc.make_kdtree(cloud)
+    rng = np.random.RandomState(args.seed)
+    t0 = time.perf_counter()
+    items = [orc.assemble_query(cloud, kd, qpts[i], 300, 1000, rng, bool(v['uniform_subsample'])) for i in sel]
+    patch = np.stack([it['patch_pts_ps'] for it in items])
+    sub = np.stack([it['pts_sub_sample_ms'] for it in items])
+    rad = np.array([it['patch_radius_ms'] for it in items])
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    logits = orc.model_forward(sd, patch, sub, qpts[sel], v['use_point_stn'], v['shared_transformer'])
+    sdf = orc.post_process(logits, rad)
+    t_net = time.perf_counter() - t0
+    # candidate grid is a per-shape cost: charge the sample its share
+    total = t_asm + t_net + t_grid * (n_queries / max(Q, 1))
+    return dict(value=n_queries / total, cores=cores, Q=Q, t_assemble_s=t_asm, t_network_s=t_net,
+                t_grid_s=t_grid, sdf_checksum=float(np.abs(sdf).sum()))
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cloud, sd = make_workload(args, 0)
+    rates = []
+    r = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_rate(args, cloud, sd, args.cpu_sample)
+        if i >= args.warmup:
+            rates.append(r['value'])
+    value = float(np.mean(rates))
+    line = {
+        'impl': 'reference', 'metric': 'SDF queries/sec at grid_res=%d' % args.grid_res, 'value': value,
+        'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * args.cpu_sample / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, r['Q']),
+        'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': r['cores'], 'kind': 'port',
+                         'sample': '%d queries evenly spaced over the %d-query band per step (oracle port: scipy cKDTree kNN, '
+                                   'NumPy RandomState sub-sample, torch-CPU fp32 network)' % (args.cpu_sample, r['Q'])},
+        'e2e': {'value': value, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, Q):
+    return {'workload': '%s model, 1 synthetic %d-pt cloud per GPU, grid_res=%d, epsilon=%d, kNN 300 + 1000-pt sub-sample'
+                        % (args.model, args.points, args.grid_res, args.epsilon),
+            'queries_per_shape': int(Q), 'l2': 'flushed between timed iterations (256 MiB write)'}
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for j, n in enumerate(names) if any(s[2 + j].lower().startswith('active') for s in self.samples if len(s) > 2 + j)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from points2surf_b200 import ops, synth, _lib
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    v = synth.VARIANTS[args.model]
+    cloud, sd = make_workload(args, rank)
+    precision = args.precision
+    if precision == 'auto':
+        precision = 'tc' if _lib.load().p2s_abi_version() and tc_available() else 'fp32'
+    guard = args.guard_band if args.guard_band is not None else (0.05 if precision == 'tc' else 0.0)
+
+    # calibrate the output bias on the GPU (fp32 path) so the rand-init net has mixed sign classes
+    eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision='fp32')
+    cal = synth.make_model_inputs(64, seed=777)
+    raw = eng.forward(*(torch.from_numpy(cal[k]).to(dev) for k in ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms')))
+    fc4_bias = (sd['fc4.bias'].numpy() - raw.median(dim=0).values.cpu().numpy()).astype(np.float32)
+    eng.close()
+    sd['fc4.bias'] = torch.from_numpy(fc4_bias)
+    eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
+
+    pts = torch.from_numpy(cloud).to(dev)
+    Q = int(ops.query_grid(pts, args.grid_res, args.epsilon).numel())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_cloud = torch.from_numpy(cloud).pin_memory()
+    host_lin = torch.empty(Q, dtype=torch.int32).pin_memory()
+    host_sdf = torch.empty(Q, dtype=torch.float32).pin_memory()
+
+    def step_dev():
+        return eng.reconstruct(pts, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q)
+
+    def step_host():
+        return eng.reconstruct_host(host_cloud.numpy(), args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q,
+                                    out_lin=host_lin.numpy(), out_sdf=host_sdf.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, host=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ops.launch_count(reset=True)
+        prof_reset()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            if host:
+                t0 = time.perf_counter()
+                fn()
+                total_ms += (time.perf_counter() - t0) * 1e3     # the host call returns after its D2H completed
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                total_ms += e0.elapsed_time(e1)
+        barrier()
+        launches = ops.launch_count()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_ms, launches = timed(step_dev, args.steps, max(args.warmup, 3))
+    prof = prof_get()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
+    guard_frac = eng.last_guard_count() / max(Q, 1) if precision == 'tc' else 0.0
+
+    q_total = torch.tensor([Q], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(q_total)
+    q_total = float(q_total.item())
+    value = q_total * args.steps / (dev_ms * 1e-3)
+    e2e_value = q_total * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        roofline = None
+        if prof and prof['launches'] > 0:
+            peak = peaks.get('bf16_tflops_sustained') or 1400.0
+            ach = prof['flops'] / (prof['ms'] * 1e-3) / 1e12
+            roofline = {'bound': 'tensor', 'kernel': prof['kernel'], 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': ach / peak, 'traffic': None,
+                        'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
+                        'flops_per_launch': prof['flops'] / prof['launches'], 'ms_per_launch': prof['ms'] / prof['launches'],
+                        'share_of_step': prof['ms'] / dev_ms}
+        cpu = cpu_reference_rate(args, cloud, sd, args.cpu_sample, fc4_bias=fc4_bias)
+        line = {
+            'metric': 'SDF queries/sec at grid_res=%d' % args.grid_res, 'value': value, 'unit': 'queries/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16 operands / f32 accumulate (tcgen05); f32 FC tails' if precision == 'tc' else 'f32',
+            'data': 'synthetic', 'config': dict(workload_config(args, Q), precision=precision, guard_band=guard,
+                                                guard_recompute_fraction=guard_frac),
+            'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(cloud.nbytes), 'd2h_bytes_per_step': int(Q * 8)},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'roofline': roofline,
+            'cpu_baseline': {'value': cpu['value'], 'unit': 'queries/s', 'cores': cpu['cores'], 'kind': 'port',
+                             'sample': '%d queries evenly spaced over the band (assemble %.2fs, network %.2fs)'
+                                       % (args.cpu_sample, cpu['t_assemble_s'], cpu['t_network_s'])},
+            'tensor_flops_per_s': value * FLOP_PER_QUERY[args.model],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tc_available():
+    return hasattr(__import__('points2surf_b200._lib', fromlist=['x']).load(), 'p2s_profile_get')
+
+
+def prof_reset():
+    from points2surf_b200 import _lib
+    lib = _lib.load()
+    if hasattr(lib, 'p2s_profile_reset'):
+        lib.p2s_profile_reset()
+
+
+def prof_get():
+    from points2surf_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    if not hasattr(lib, 'p2s_profile_get'):
+        return None
+    ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+    lib.p2s_profile_get(C.byref(ms), C.byref(n), C.byref(fl))
+    return {'ms': ms.value, 'launches': n.value, 'flops': fl.value, 'kernel': 'pointnet_pass_tc'}
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

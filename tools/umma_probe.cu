@@ -1,0 +1,297 @@
+// Standalone probe for the tcgen05 building blocks used by net_tc.cu.  Run on a B200:
+//   tools/bin/umma_probe
+// 1. correctness of the no-swizzle K-major smem descriptors (which LBO/SBO convention is right),
+// 2. A-operand-from-TMEM layout, 3. bulk copy + mbarrier, 4. MMA issue rate (SS vs TS, N=128/256),
+// 5. TMEM->register epilogue cost with a 3-input max reduction.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include <cuda_runtime.h>
+#include "../points2surf_b200/csrc/tc_ptx.cuh"
+
+using namespace p2s::ptx;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+// bounded mbarrier wait: a wrong barrier protocol must not hang the box
+__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("TIMEOUT waiting on mbarrier (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+#define mbar_wait wait_or_trap
+
+__device__ __forceinline__ uint32_t kmajor_off(int r, int k, uint32_t lbo, uint32_t sbo) {
+    return (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * lbo + (uint32_t)(r & 7) * 16 + (uint32_t)(k & 7) * 2;
+}
+
+struct GemmCfg {
+    int M, N, K;
+    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // physical layout strides (bytes)
+    int swap_fields;                        // put LBO in the SBO field and vice versa
+    int a_from_tmem;
+    int use_bulk;                           // stage B through a global buffer + cp.async.bulk
+};
+
+// one CTA, 128 threads: D[M=128][N] = A[128][K] * B[N][K]^T
+__global__ void __launch_bounds__(128) gemm_probe(GemmCfg c, const __half* __restrict__ A, const __half* __restrict__ B,
+                                                  const uint8_t* __restrict__ B_packed, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma, bar_tx;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 65536;
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_tx, 1); fence_mbar_init(); }
+    for (int e = tid; e < c.M * c.K; e += 128) {
+        int r = e / c.K, k = e % c.K;
+        *reinterpret_cast<__half*>(sA + kmajor_off(r, k, c.a_lbo, c.a_sbo)) = A[e];
+    }
+    if (!c.use_bulk) {
+        for (int e = tid; e < c.N * c.K; e += 128) {
+            int r = e / c.K, k = e % c.K;
+            *reinterpret_cast<__half*>(sB + kmajor_off(r, k, c.b_lbo, c.b_sbo)) = B[e];
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (c.use_bulk) {
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)(c.N * c.K * 2);
+            mbar_arrive_expect_tx(&bar_tx, bytes);
+            bulk_g2s(sB, B_packed, bytes, &bar_tx);
+        }
+        mbar_wait(&bar_tx, 0);
+    }
+    const uint32_t a_col = 256;  // TMEM columns for the A operand (TS mode)
+    if (c.a_from_tmem) {
+        // lane = row; column j holds K elements 2j, 2j+1
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + a_col;
+        for (int j0 = 0; j0 < c.K / 2; j0 += 8) {
+            uint32_t v[8];
+            for (int j = 0; j < 8; ++j) {
+                __half2 h = __halves2half2(A[tid * c.K + 2 * (j0 + j)], A[tid * c.K + 2 * (j0 + j) + 1]);
+                v[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            tmem_st_x8(taddr + j0, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_f16(c.M, c.N);
+        for (int ks = 0; ks < c.K / 16; ++ks) {
+            uint32_t a_addr = smem_u32(sA) + ks * 2 * c.a_lbo;
+            uint32_t b_addr = smem_u32(sB) + ks * 2 * c.b_lbo;
+            uint64_t da = c.swap_fields ? make_smem_desc(a_addr, c.a_sbo, c.a_lbo) : make_smem_desc(a_addr, c.a_lbo, c.a_sbo);
+            uint64_t db = c.swap_fields ? make_smem_desc(b_addr, c.b_sbo, c.b_lbo) : make_smem_desc(b_addr, c.b_lbo, c.b_sbo);
+            if (c.a_from_tmem) mma_ts(tmem, tmem + a_col + ks * 8, db, idesc, ks > 0);
+            else mma_ss(tmem, da, db, idesc, ks > 0);
+        }
+        mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int n0 = 0; n0 < c.N; n0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem + ((uint32_t)(warp * 32) << 16) + n0, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) D[tid * c.N + n0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// throughput probe: every CTA issues reps x (K=128 -> 8 MMAs of M=128 x N) back to back
+struct RateCfg { int N; int ts; int reps; int epi; };
+
+__global__ void __launch_bounds__(192) rate_probe(RateCfg c, long long* cycles_out, long long* epi_out, float* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma[2], bar_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // A: 128 x 128 fp16 (32 KB) at 0, B: 256 x 128 fp16 (64 KB) at 32 KB ; LBO=128, SBO=2048 (K=128)
+    for (int e = tid; e < (32768 + 65536) / 4; e += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u ^ ((e * 2654435761u) & 0x03ff03ffu);  // halves near 1.0
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1); mbar_init(&bar_empty[0], 128); mbar_init(&bar_empty[1], 128); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (c.ts && warp < 4) {
+        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) v[j] = 0x3c003800u + j;
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + 448, v);
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + 480, v);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, c.N);
+    const uint32_t stage_cols = (c.N <= 128) ? 128 : 256;   // two accumulator stages
+    long long t0 = 0, t1 = 0;
+    if (warp == 4) {
+        if ((tid & 31) == 0) {
+            t0 = clock64();
+            for (int rep = 0; rep < c.reps; ++rep) {
+                const int s = rep & 1;
+                if (c.epi) mbar_wait(&bar_empty[s], ((rep >> 1) & 1) ^ 1);   // epilogue drained this stage
+                tc_fence_after();
+                uint32_t d = tmem + ((c.ts && c.N > 128) ? 0 : s * stage_cols);
+                for (int ks = 0; ks < 8; ++ks) {
+                    uint64_t da = make_smem_desc(smem_u32(smem) + ks * 256, 128, 2048);
+                    uint64_t db = make_smem_desc(smem_u32(smem + 32768) + ks * 256, 128, 2048);
+                    if (c.ts) mma_ts(d, tmem + 448 + ks * 8, db, idesc, 1);
+                    else mma_ss(d, da, db, idesc, 1);
+                }
+                if (c.epi) mma_commit(&bar_mma[s]);
+            }
+            if (!c.epi) mma_commit(&bar_mma[0]);
+            else {
+                mbar_wait(&bar_mma[(c.reps - 1) & 1], ((c.reps - 1) >> 1) & 1);
+            }
+            if (c.epi) { t1 = clock64(); cycles_out[blockIdx.x] = t1 - t0; }
+        }
+    }
+    if (!c.epi) {
+        mbar_wait(&bar_mma[0], 0);
+        if (tid == 128) { t1 = clock64(); cycles_out[blockIdx.x] = t1 - t0; }
+    } else if (warp < 4) {
+        float acc = -INFINITY;
+        long long e0 = clock64();
+        for (int rep = 0; rep < c.reps; ++rep) {
+            const int s = rep & 1;
+            mbar_wait(&bar_mma[s], (rep >> 1) & 1);
+            tc_fence_after();
+            uint32_t d = tmem + ((uint32_t)(warp * 32) << 16) + s * stage_cols;
+            for (int n0 = 0; n0 < c.N; n0 += 32) {
+                uint32_t r[32];
+                tmem_ld_x32(d + n0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) acc = fmax3(acc, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_empty[s]);
+        }
+        long long e1 = clock64();
+        if (tid == 0) epi_out[blockIdx.x] = e1 - e0;
+        sink[blockIdx.x * 128 + tid] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void run_gemm(const char* name, GemmCfg c) {
+    std::vector<__half> hA(c.M * c.K), hB(c.N * c.K);
+    std::vector<float> fA(c.M * c.K), fB(c.N * c.K);
+    srand(1);
+    for (size_t i = 0; i < hA.size(); ++i) { fA[i] = (float)(rand() % 5 - 2); hA[i] = __float2half(fA[i]); }
+    for (size_t i = 0; i < hB.size(); ++i) { fB[i] = (float)(rand() % 7 - 3); hB[i] = __float2half(fB[i]); }
+    // packed image of B in the physical layout (for the bulk-copy variant)
+    std::vector<uint8_t> packed(c.N * c.K * 2, 0);
+    for (int r = 0; r < c.N; ++r)
+        for (int k = 0; k < c.K; ++k) {
+            uint32_t off = (uint32_t)(r >> 3) * c.b_sbo + (uint32_t)(k >> 3) * c.b_lbo + (r & 7) * 16 + (k & 7) * 2;
+            if (off + 2 <= packed.size()) *reinterpret_cast<__half*>(&packed[off]) = hB[r * c.K + k];
+        }
+    __half *dA, *dB; uint8_t* dP; float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dP, packed.size()));
+    CK(cudaMalloc(&dD, c.M * c.N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dP, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, c.M * c.N * 4));
+    CK(cudaFuncSetAttribute(gemm_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    gemm_probe<<<1, 128, 131072>>>(c, dA, dB, dP, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    std::vector<float> hD(c.M * c.N);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0; int bad = 0;
+    for (int m = 0; m < c.M; ++m)
+        for (int n = 0; n < c.N; ++n) {
+            float ref = 0;
+            for (int k = 0; k < c.K; ++k) ref += fA[m * c.K + k] * fB[n * c.K + k];
+            double err = fabs((double)hD[m * c.N + n] - ref);
+            if (!(err <= 1e-3)) ++bad;
+            if (err > maxerr || err != err) maxerr = err;
+        }
+    printf("%-44s : max_err %.4g  bad %d / %d  %s\n", name, maxerr, bad, c.M * c.N, bad == 0 ? "OK" : "WRONG");
+    cudaFree(dA); cudaFree(dB); cudaFree(dP); cudaFree(dD);
+}
+
+static void run_rate(const char* name, RateCfg c, int grid) {
+    long long *dC, *dE; float* dS;
+    CK(cudaMalloc(&dC, grid * 8)); CK(cudaMalloc(&dE, grid * 8)); CK(cudaMalloc(&dS, grid * 128 * 4));
+    CK(cudaMemset(dC, 0, grid * 8)); CK(cudaMemset(dE, 0, grid * 8));
+    CK(cudaFuncSetAttribute(rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    rate_probe<<<grid, 192, 32768 + 65536>>>(c, dC, dE, dS);  // warm-up
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    rate_probe<<<grid, 192, 32768 + 65536>>>(c, dC, dE, dS);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> hC(grid), hE(grid);
+    CK(cudaMemcpy(hC.data(), dC, grid * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hE.data(), dE, grid * 8, cudaMemcpyDeviceToHost));
+    long long mn = hC[0], mx = hC[0];
+    for (int i = 0; i < grid; ++i) { if (hC[i] < mn) mn = hC[i]; if (hC[i] > mx) mx = hC[i]; }
+    double per_mma = (double)mx / (c.reps * 8.0);
+    double flops = 2.0 * 128 * c.N * 128 * (double)c.reps * grid;
+    printf("%-44s : cycles/MMA(K16) min %.1f max %.1f | epi cycles/tile %.0f | kernel %.3f ms -> %.1f TFLOP/s\n", name,
+           (double)mn / (c.reps * 8.0), per_mma, c.epi ? (double)hE[0] / c.reps : 0.0, ms, flops / (ms * 1e-3) / 1e12);
+    cudaFree(dC); cudaFree(dE); cudaFree(dS);
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    printf("device %s sm_%d%d SMs %d\n", p.name, p.major, p.minor, p.multiProcessorCount);
+    const int M = 128, N = 64, K = 64;
+    // layout A: [r/8][k/8] (SBO = K/8*128, LBO = 128); layout B: [k/8][r/8] (LBO = R/8*128, SBO = 128)
+    GemmCfg a{M, N, K, 128, (uint32_t)(K / 8 * 128), 128, (uint32_t)(K / 8 * 128), 0, 0, 0};
+    run_gemm("SS layoutA fields(lbo,sbo)", a);
+    a.swap_fields = 1; run_gemm("SS layoutA fields swapped", a);
+    GemmCfg b{M, N, K, (uint32_t)(M / 8 * 128), 128, (uint32_t)(N / 8 * 128), 128, 0, 0, 0};
+    run_gemm("SS layoutB fields(lbo,sbo)", b);
+    b.swap_fields = 1; run_gemm("SS layoutB fields swapped", b);
+    GemmCfg t{M, N, K, 128, (uint32_t)(K / 8 * 128), 128, (uint32_t)(K / 8 * 128), 0, 1, 0};
+    run_gemm("TS (A in TMEM) layoutA", t);
+    t.swap_fields = 1; run_gemm("TS (A in TMEM) layoutA swapped", t);
+    GemmCfg u{M, N, K, 128, (uint32_t)(K / 8 * 128), 128, (uint32_t)(K / 8 * 128), 0, 0, 1};
+    run_gemm("SS layoutA, B via cp.async.bulk", u);
+    u.swap_fields = 1; run_gemm("SS layoutA swapped, B via cp.async.bulk", u);
+    GemmCfg w{128, 256, 128, 128, 2048, 128, 2048, 0, 0, 0};
+    run_gemm("SS layoutA M128 N256 K128", w);
+    w.swap_fields = 1; run_gemm("SS layoutA swapped M128 N256 K128", w);
+    GemmCfg x{128, 256, 128, 128, 2048, 128, 2048, 0, 1, 0};
+    run_gemm("TS layoutA M128 N256 K128", x);
+
+    const int grid = p.multiProcessorCount;
+    run_rate("rate SS N=256 (1 CTA)", RateCfg{256, 0, 256, 0}, 1);
+    run_rate("rate SS N=256 (all SMs)", RateCfg{256, 0, 256, 0}, grid);
+    run_rate("rate SS N=128 (all SMs)", RateCfg{128, 0, 256, 0}, grid);
+    run_rate("rate TS N=256 (all SMs)", RateCfg{256, 1, 256, 0}, grid);
+    run_rate("rate TS N=128 (all SMs)", RateCfg{128, 1, 256, 0}, grid);
+    run_rate("rate SS N=128 + max epilogue (all SMs)", RateCfg{128, 0, 256, 1}, grid);
+    run_rate("rate TS N=128 + max epilogue (all SMs)", RateCfg{128, 1, 256, 1}, grid);
+    run_rate("rate SS N=256 + max epilogue (all SMs)", RateCfg{256, 0, 256, 1}, grid);
+    return 0;
+}
