@@ -45,7 +45,7 @@ def parse():
     ap.add_argument('--points', type=int, default=10000)
     ap.add_argument('--precision', default='auto', choices=['auto', 'tc', 'fp32'])
     ap.add_argument('--guard_band', type=float, default=None)
-    ap.add_argument('--cpu_sample', type=int, default=48, help='queries in the bounded CPU-baseline sample')
+    ap.add_argument('--cpu_sample', type=int, default=256, help='queries in the bounded CPU-baseline sample')
     ap.add_argument('--seed', type=int, default=40938661)
     return ap.parse_args()
 

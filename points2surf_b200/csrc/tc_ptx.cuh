@@ -70,6 +70,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
     return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// 128-byte swizzled K-major operand (rows of 64 fp16 = 128 B, 8-row atoms of 1024 B, 16-B chunk index XOR row%8);
+// start address 1024-B aligned (+32 B per K=16 step inside the atom), SBO = 1024, LBO unused (1).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
 // Instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 accumulate, MxN tile.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4)            // c_format = F32

@@ -78,6 +78,8 @@ class Engine:
         if pa.shape != (B, self.P, 3) or su.shape != (B, self.S, 3) or qu.shape != (B, 3):
             raise P2SError('bad input shapes %s %s %s' % (tuple(pa.shape), tuple(su.shape), tuple(qu.shape)))
         out = torch.empty((B, 2), dtype=torch.float32, device=pa.device)
+        if B == 0:
+            return out
         with torch.cuda.device(pa.device):
             check(self.lib.p2s_forward_dev(self.handle, _ptr(pa), _ptr(su), _ptr(qu), B, _ptr(out), _stream()))
         return out

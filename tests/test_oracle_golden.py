@@ -75,3 +75,35 @@ def test_sign_propagation_golden():
 def test_all_zero_distances_are_skipped():
     q = orc.query_grid(synth.make_cloud('sphere', 500, seed=1), 16, 3)
     assert orc.sdf_to_volume(np.zeros(len(q), np.float32), q, 16, 5, 13) is None
+
+
+def test_marching_cubes_oracle_sphere_is_closed_and_accurate():
+    from oracle import mc_oracle as mc
+    R = 24
+    g = (np.arange(R) + 0.5) / R * 2 - 1
+    X, Y, Z = np.meshgrid(g, g, g, indexing='ij')
+    vol = (0.6 - np.sqrt(X ** 2 + Y ** 2 + Z ** 2)).astype(np.float32)
+    v, f = mc.marching_cubes(vol)
+    assert mc.mesh_is_closed(f) and len(v) - 3 * len(f) // 2 + len(f) == 2       # Euler characteristic of a sphere
+    r = np.linalg.norm(v, axis=1)
+    assert abs(r - 0.6).max() < 0.5 * (2.0 / R) ** 2 + 1e-3                      # linear interpolation error
+    a, b, c = (v[f[:, i]].astype(np.float64) for i in range(3))
+    assert np.einsum('ij,ij->i', a, np.cross(b, c)).sum() > 0                    # outward orientation
+    # Chamfer (reference definition) between the mesh and the analytic sphere, 10k samples each side
+    rng = np.random.RandomState(0)
+    s_mesh = orc.sample_mesh_surface(v, f, 10000, rng)
+    d = rng.standard_normal((10000, 3))
+    s_ref = 0.6 * d / np.linalg.norm(d, axis=1, keepdims=True)
+    assert orc.chamfer(s_mesh, s_ref) / 20000 < 0.02
+
+
+def test_marching_cubes_oracle_handles_zeros_and_noise():
+    from oracle import mc_oracle as mc
+    rng = np.random.RandomState(0)
+    vol = rng.standard_normal((12, 12, 12)).astype(np.float32)
+    vol[[0, -1], :, :] = -1; vol[:, [0, -1], :] = -1; vol[:, :, [0, -1]] = -1
+    vol[3, 3, 3] = 0; vol[5, 5, 5] = 0
+    v, f = mc.marching_cubes(vol)
+    assert mc.mesh_is_closed(f) and np.isfinite(v).all()
+    v2, f2 = mc.marching_cubes(np.full((8, 8, 8), -1.0, np.float32))
+    assert len(v2) == 0 and len(f2) == 0

@@ -261,7 +261,156 @@ static void run_rate(const char* name, RateCfg c, int grid) {
     cudaFree(dC); cudaFree(dE); cudaFree(dS);
 }
 
-int main() {
+
+// ---------------------------------------------------------------------------------------------------
+// SWIZZLE_128B K-major correctness: D[128][N] = A[128][K] B[N][K]^T with K = 64 * katoms
+__device__ __forceinline__ uint32_t sw128_off(int r, int k, int rows) {
+    int atom = k >> 6, kk = k & 63, chunk = kk >> 3;
+    return (uint32_t)atom * (uint32_t)rows * 128u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+           (uint32_t)((chunk ^ (r & 7)) * 16) + (uint32_t)(kk & 7) * 2u;
+}
+__global__ void __launch_bounds__(128) gemm_sw128_probe(int N, int K, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 65536;
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
+    for (int e = tid; e < 128 * K; e += 128) *reinterpret_cast<__half*>(sA + sw128_off(e / K, e % K, 128)) = A[e];
+    for (int e = tid; e < N * K; e += 128) *reinterpret_cast<__half*>(sB + sw128_off(e / K, e % K, N)) = B[e];
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_f16(128, N);
+        for (int ks = 0; ks < K / 16; ++ks) {
+            uint32_t a_addr = smem_u32(sA) + (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+            uint32_t b_addr = smem_u32(sB) + (ks >> 2) * N * 128 + (ks & 3) * 32;
+            mma_ss(tmem, make_smem_desc_sw128(a_addr), make_smem_desc_sw128(b_addr), idesc, ks > 0);
+        }
+        mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int n0 = 0; n0 < N; n0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem + ((uint32_t)(warp * 32) << 16) + n0, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) D[tid * N + n0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void run_gemm_sw128(const char* name, int N, int K) {
+    std::vector<__half> hA(128 * K), hB(N * K);
+    std::vector<float> fA(128 * K), fB(N * K);
+    srand(2);
+    for (size_t i = 0; i < hA.size(); ++i) { fA[i] = (float)(rand() % 5 - 2); hA[i] = __float2half(fA[i]); }
+    for (size_t i = 0; i < hB.size(); ++i) { fB[i] = (float)(rand() % 7 - 3); hB[i] = __float2half(fB[i]); }
+    __half *dA, *dB; float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(gemm_sw128_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    gemm_sw128_probe<<<1, 128, 131072>>>(N, K, dA, dB, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    std::vector<float> hD(128 * N);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0; double maxerr = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float ref = 0;
+            for (int k = 0; k < K; ++k) ref += fA[m * K + k] * fB[n * K + k];
+            double err = fabs((double)hD[m * N + n] - ref);
+            if (!(err <= 1e-3)) ++bad;
+            if (err > maxerr || err != err) maxerr = err;
+        }
+    printf("%-44s : max_err %.4g  bad %d / %d  %s\n", name, maxerr, bad, 128 * N, bad == 0 ? "OK" : "WRONG");
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
+// generalised issue-rate probe: K=128 (8 MMAs) per rep, A 128x128, B Nx128
+struct Rate2 { int N; int ts; int layout; int alt; int reps; };   // layout 0: LBO128/SBO2048, 1: LBO rows*16/SBO128, 2: SW128
+__global__ void __launch_bounds__(160) rate2_probe(Rate2 c, long long* cycles_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (32768 + 65536) / 4; e += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u ^ ((e * 2654435761u) & 0x03ff03ffu);
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (c.ts && warp < 4) {
+        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) v[j] = 0x3c003800u + j;
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + 448, v);
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + 480, v);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, c.N);
+    if (tid == 128) {
+        const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32768);
+        long long t0 = clock64();
+        for (int rep = 0; rep < c.reps; ++rep) {
+            for (int ks = 0; ks < 8; ++ks) {
+                uint64_t da, db;
+                if (c.layout == 0) { da = make_smem_desc(sa + ks * 256, 128, 2048); db = make_smem_desc(sb + ks * 256, 128, 2048); }
+                else if (c.layout == 1) { da = make_smem_desc(sa + ks * 4096, 2048, 128); db = make_smem_desc(sb + ks * 2 * c.N * 16, c.N * 16, 128); }
+                else { da = make_smem_desc_sw128(sa + (ks >> 2) * 16384 + (ks & 3) * 32); db = make_smem_desc_sw128(sb + (ks >> 2) * c.N * 128 + (ks & 3) * 32); }
+                uint32_t d = tmem;
+                if (c.alt && c.N <= 192) d += ((rep * 8 + ks) & 1) * 192;
+                if (c.ts) mma_ts(d, tmem + 448 + ks * 8, db, idesc, 1);
+                else mma_ss(d, da, db, idesc, 1);
+            }
+        }
+        mma_commit(&bar_mma);
+        mbar_wait(&bar_mma, 0);
+        cycles_out[blockIdx.x] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void run_rate2(const char* name, Rate2 c, int grid) {
+    long long* dC;
+    CK(cudaMalloc(&dC, grid * 8));
+    CK(cudaFuncSetAttribute(rate2_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    rate2_probe<<<grid, 160, 32768 + 65536>>>(c, dC);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    rate2_probe<<<grid, 160, 32768 + 65536>>>(c, dC);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> hC(grid);
+    CK(cudaMemcpy(hC.data(), dC, grid * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < grid; ++i) if (hC[i] > mx) mx = hC[i];
+    double ideal = 128.0 * c.N / 256.0;
+    printf("%-44s : cycles/MMA %.1f (ideal %.0f, eff %.0f%%) kernel %.3f ms -> %.0f TFLOP/s\n", name, (double)mx / (c.reps * 8.0), ideal,
+           100.0 * ideal / ((double)mx / (c.reps * 8.0)), ms, 2.0 * 128 * c.N * 128 * (double)c.reps * grid / (ms * 1e-3) / 1e12);
+    cudaFree(dC);
+}
+
+int main(int argc, char** argv) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     printf("device %s sm_%d%d SMs %d\n", p.name, p.major, p.minor, p.multiProcessorCount);
     const int M = 128, N = 64, K = 64;
@@ -293,5 +442,21 @@ int main() {
     run_rate("rate SS N=128 + max epilogue (all SMs)", RateCfg{128, 0, 256, 1}, grid);
     run_rate("rate TS N=128 + max epilogue (all SMs)", RateCfg{128, 1, 256, 1}, grid);
     run_rate("rate SS N=256 + max epilogue (all SMs)", RateCfg{256, 0, 256, 1}, grid);
+    run_gemm_sw128("SS SW128 N=64 K=64", 64, 64);
+    run_gemm_sw128("SS SW128 N=256 K=128", 256, 128);
+    run_rate2("r2 SS nosw layoutA N=256", Rate2{256, 0, 0, 0, 256}, grid);
+    run_rate2("r2 SS nosw layoutB N=256", Rate2{256, 0, 1, 0, 256}, grid);
+    run_rate2("r2 SS SW128 N=256", Rate2{256, 0, 2, 0, 256}, grid);
+    run_rate2("r2 SS SW128 N=128", Rate2{128, 0, 2, 0, 256}, grid);
+    run_rate2("r2 SS SW128 N=128 alt-acc", Rate2{128, 0, 2, 1, 256}, grid);
+    run_rate2("r2 SS SW128 N=192", Rate2{192, 0, 2, 0, 256}, grid);
+    run_rate2("r2 SS SW128 N=64", Rate2{64, 0, 2, 0, 256}, grid);
+    run_rate2("r2 TS SW128 N=256", Rate2{256, 1, 2, 0, 256}, grid);
+    run_rate2("r2 TS SW128 N=128", Rate2{128, 1, 2, 0, 256}, grid);
+    run_rate2("r2 TS SW128 N=128 alt-acc", Rate2{128, 1, 2, 1, 256}, grid);
+    run_rate2("r2 TS SW128 N=64", Rate2{64, 1, 2, 0, 256}, grid);
+    run_rate2("r2 TS nosw N=128 alt-acc", Rate2{128, 1, 0, 1, 256}, grid);
+    run_rate2("r2 TS nosw N=192", Rate2{192, 1, 0, 0, 256}, grid);
+    run_rate2("r2 SS nosw N=64", Rate2{64, 0, 0, 0, 256}, grid);
     return 0;
 }
