@@ -37,41 +37,9 @@ def make_train_opt(variant='vanilla', points_per_patch=300, sub_sample_size=1000
 
 
 def _layer_specs(variant, net=1024):
-    """(prefix, kind, cout, cin) in the reference's registration order
-    (source/points_to_surf_model.py:12-36,72-99,134-167,237-294)."""
+    from .arch import layer_specs
     v = VARIANTS[variant]
-
-    def stn(prefix, dim, quat):
-        out = 4 if quat else dim * dim
-        return [(prefix + 'conv1', 'conv', 64, dim), (prefix + 'conv2', 'conv', 128, 64),
-                (prefix + 'conv3', 'conv', net, 128),
-                (prefix + 'fc1', 'fc', net // 2, net), (prefix + 'fc2', 'fc', net // 4, net // 2),
-                (prefix + 'fc3', 'fc', out, net // 4),
-                (prefix + 'bn1', 'bn', 64, 0), (prefix + 'bn2', 'bn', 128, 0), (prefix + 'bn3', 'bn', net, 0),
-                (prefix + 'bn4', 'bn', net // 2, 0), (prefix + 'bn5', 'bn', net // 4, 0)]
-
-    def feat(prefix, point_stn):
-        s = []
-        if point_stn:
-            s += stn(prefix + 'stn1.', 3, True)
-        s += stn(prefix + 'stn2.', 64, False)
-        s += [(prefix + 'conv0a', 'conv', 64, 3), (prefix + 'conv0b', 'conv', 64, 64),
-              (prefix + 'bn0a', 'bn', 64, 0), (prefix + 'bn0b', 'bn', 64, 0),
-              (prefix + 'conv1', 'conv', 64, 64), (prefix + 'conv2', 'conv', 128, 64),
-              (prefix + 'conv3', 'conv', net, 128),
-              (prefix + 'bn1', 'bn', 64, 0), (prefix + 'bn2', 'bn', 128, 0), (prefix + 'bn3', 'bn', net, 0)]
-        return s
-
-    specs = []
-    if v['use_point_stn'] and v['shared_transformer']:
-        specs += stn('point_stn.', 3, True)
-    specs += feat('feat_local.', False)
-    specs += feat('feat_global.', bool(v['use_point_stn'] and not v['shared_transformer']))
-    specs += [('fc1_local', 'fc', net // 2, net), ('fc1_global', 'fc', net // 2, net),
-              ('bn1_local', 'bn', net // 2, 0), ('bn1_global', 'bn', net // 2, 0),
-              ('fc2', 'fc', net // 4, net), ('fc3', 'fc', net // 8, net // 4), ('fc4', 'fc', 2, net // 8),
-              ('bn2', 'bn', net // 4, 0), ('bn3', 'bn', net // 8, 0)]
-    return specs
+    return layer_specs(v['use_point_stn'], v['shared_transformer'], net)
 
 
 def make_state_dict_numpy(variant='vanilla', seed=0, net=1024, module_prefix=''):
