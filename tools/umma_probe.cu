@@ -410,9 +410,131 @@ static void run_rate2(const char* name, Rate2 c, int grid) {
     cudaFree(dC);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// probe 3: tight issue loop (descriptors precomputed, compile-time shape) -- the real tensor-pipe rate
+template <int N, bool TS, bool EPI>
+__global__ void __launch_bounds__(192) rate3_probe(int reps, long long* cycles_out, float* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_full[2], bar_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (32768 + 65536) / 4; e += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u ^ ((e * 2654435761u) & 0x03ff03ffu);
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_empty[0], 128); mbar_init(&bar_empty[1], 128); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t kStage = (N <= 128) ? 128 : 256;
+    constexpr uint32_t kACol = 2 * kStage;    // A operand columns (TS); only valid when N <= 128 or !EPI
+    if (TS && warp < 4) {
+        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) v[j] = 0x3c003800u + j;
+        const uint32_t col = (N <= 128) ? kACol : 448;
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + col, v);
+        tmem_st_x32(tmem + ((uint32_t)(warp * 32) << 16) + col + 32, v);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(128, N);
+    if (warp == 4) {
+        if ((tid & 31) == 0) {
+            uint64_t da[8], db[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                da[ks] = make_smem_desc(smem_u32(smem) + ks * 256, 128, 2048);
+                db[ks] = make_smem_desc(smem_u32(smem + 32768) + ks * 256, 128, 2048);
+            }
+            const uint32_t acol = tmem + ((N <= 128) ? kACol : 448);
+            long long t0 = clock64();
+            for (int rep = 0; rep < reps; ++rep) {
+                const int s = rep & 1;
+                if (EPI) { mbar_wait(&bar_empty[s], ((rep >> 1) & 1) ^ 1); tc_fence_after(); }
+                const uint32_t d = tmem + ((TS && N > 128) ? 0 : s * kStage);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (TS) mma_ts(d, acol + ks * 8, db[ks], idesc, 1);
+                    else mma_ss(d, da[ks], db[ks], idesc, 1);
+                }
+                if (EPI) mma_commit(&bar_full[s]);
+            }
+            if (!EPI) { mma_commit(&bar_full[0]); mbar_wait(&bar_full[0], 0); }
+            else mbar_wait(&bar_full[(reps - 1) & 1], ((reps - 1) >> 1) & 1);
+            cycles_out[blockIdx.x] = clock64() - t0;
+        }
+    } else if (EPI && warp < 4) {
+        float acc = -INFINITY;
+        for (int rep = 0; rep < reps; ++rep) {
+            const int s = rep & 1;
+            mbar_wait(&bar_full[s], (rep >> 1) & 1);
+            tc_fence_after();
+            const uint32_t d = tmem + ((uint32_t)(warp * 32) << 16) + s * kStage;
+#pragma unroll
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t r[32];
+                tmem_ld_x32(d + n0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) acc = fmax3(acc, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_empty[s]);
+        }
+        sink[blockIdx.x * 128 + tid] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N, bool TS, bool EPI>
+static void run_rate3(const char* name, int grid, int reps) {
+    long long* dC; float* dS;
+    CK(cudaMalloc(&dC, grid * 8)); CK(cudaMalloc(&dS, grid * 128 * 4));
+    auto k = rate3_probe<N, TS, EPI>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<<<grid, 192, 32768 + 65536>>>(reps, dC, dS);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    k<<<grid, 192, 32768 + 65536>>>(reps, dC, dS);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> hC(grid);
+    CK(cudaMemcpy(hC.data(), dC, grid * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < grid; ++i) if (hC[i] > mx) mx = hC[i];
+    double ideal = 128.0 * N / 256.0, got = (double)mx / (reps * 8.0);
+    printf("%-44s : cycles/MMA %.1f (ideal %.0f, eff %.0f%%) kernel %.3f ms -> %.0f TFLOP/s\n", name, got, ideal, 100.0 * ideal / got, ms,
+           2.0 * 128 * N * 128 * (double)reps * grid / (ms * 1e-3) / 1e12);
+    cudaFree(dC); cudaFree(dS);
+}
+
 int main(int argc, char** argv) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     printf("device %s sm_%d%d SMs %d\n", p.name, p.major, p.minor, p.multiProcessorCount);
+    if (argc > 1 && atoi(argv[1]) == 3) {
+        const int g = p.multiProcessorCount;
+        run_rate3<256, false, false>("r3 SS N=256", g, 512);
+        run_rate3<128, false, false>("r3 SS N=128", g, 512);
+        run_rate3<64, false, false>("r3 SS N=64", g, 512);
+        run_rate3<256, true, false>("r3 TS N=256", g, 512);
+        run_rate3<128, true, false>("r3 TS N=128", g, 512);
+        run_rate3<64, true, false>("r3 TS N=64", g, 512);
+        run_rate3<256, false, true>("r3 SS N=256 + max epilogue", g, 512);
+        run_rate3<128, false, true>("r3 SS N=128 + max epilogue", g, 512);
+        run_rate3<128, true, true>("r3 TS N=128 + max epilogue", g, 512);
+        run_rate3<64, true, true>("r3 TS N=64 + max epilogue", g, 512);
+        run_rate3<256, false, true>("r3 SS N=256 + max epilogue, 20k reps (sustained)", g, 20000);
+        run_rate3<128, true, true>("r3 TS N=128 + max epilogue, 40k reps (sustained)", g, 40000);
+        return 0;
+    }
     const int M = 128, N = 64, K = 64;
     // layout A: [r/8][k/8] (SBO = K/8*128, LBO = 128); layout B: [k/8][r/8] (LBO = R/8*128, SBO = 128)
     GemmCfg a{M, N, K, 128, (uint32_t)(K / 8 * 128), 128, (uint32_t)(K / 8 * 128), 0, 0, 0};
