@@ -176,7 +176,7 @@ def run_b200(args):
     cloud, sd = make_workload(args, rank)
     precision = args.precision
     if precision == 'auto':
-        precision = 'tc' if _lib.load().p2s_abi_version() and tc_available() else 'fp32'
+        precision = 'tc'
     guard = args.guard_band if args.guard_band is not None else (0.05 if precision == 'tc' else 0.0)
 
     # calibrate the output bias on the GPU (fp32 path) so the rand-init net has mixed sign classes
@@ -212,7 +212,8 @@ def run_b200(args):
             fn()
         barrier()
         ops.launch_count(reset=True)
-        prof_reset()
+        if not host:
+            eng.profile_enable(precision == 'tc')
         total_ms = 0.0
         for _ in range(steps):
             flush.zero_()
@@ -238,7 +239,8 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     dev_ms, launches = timed(step_dev, args.steps, max(args.warmup, 3))
-    prof = prof_get()
+    prof = eng.profile_get() if precision == 'tc' else None
+    eng.profile_enable(False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
@@ -286,28 +288,6 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def tc_available():
-    return hasattr(__import__('points2surf_b200._lib', fromlist=['x']).load(), 'p2s_profile_get')
-
-
-def prof_reset():
-    from points2surf_b200 import _lib
-    lib = _lib.load()
-    if hasattr(lib, 'p2s_profile_reset'):
-        lib.p2s_profile_reset()
-
-
-def prof_get():
-    from points2surf_b200 import _lib
-    import ctypes as C
-    lib = _lib.load()
-    if not hasattr(lib, 'p2s_profile_get'):
-        return None
-    ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
-    lib.p2s_profile_get(C.byref(ms), C.byref(n), C.byref(fl))
-    return {'ms': ms.value, 'launches': n.value, 'flops': fl.value, 'kernel': 'pointnet_pass_tc'}
 
 
 if __name__ == '__main__':

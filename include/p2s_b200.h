@@ -80,6 +80,19 @@ int p2s_model_set_precision(p2s_model* m, int precision, float guard_band);
 /* number of queries the last forward recomputed on the fp32 path (guard band); sync. */
 int p2s_model_last_guard_count(p2s_model* m, int64_t* count);
 
+/* Instrumentation for bench.py's roofline: when enabled, every launch of the dominant kernel (the tensor-core
+ * PointNet pass) is bracketed by CUDA events on its stream.  p2s_profile_get synchronises on those events and
+ * returns the summed device time, the number of launches and their algorithmic FLOPs (un-padded points,
+ * SURVEY.md section 8d), then keeps accumulating until the next p2s_profile_enable call. */
+int p2s_profile_enable(p2s_model* m, int on);
+int p2s_profile_get(p2s_model* m, double* ms, int64_t* launches, double* flops);
+
+/* Diagnostic tap used by the parity tests: when `aux` (device, [B][P2S_AUX_STRIDE] floats) is non-NULL every
+ * following forward also writes, per query, the point rotation R (9), feat_local's max feature (1024) and
+ * feat_global's max feature (1024) -- trans / the PointNetfeat outputs of points_to_surf_model.py:326-343. */
+#define P2S_AUX_STRIDE 2064
+int p2s_model_set_debug_aux(p2s_model* m, float* aux);
+
 /* PointsToSurfModel.forward (source/points_to_surf_model.py:296-352), eval mode.
  *   patch_pts_ps            [B, points_per_patch, 3]   x['patch_pts_ps']
  *   pts_sub_sample_ms       [B, sub_sample_size, 3]    x['pts_sub_sample_ms'] (model space, NOT yet centred;

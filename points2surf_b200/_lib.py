@@ -35,6 +35,9 @@ SIGNATURES = {
     'p2s_model_destroy': (None, [_vp]),
     'p2s_model_set_precision': (C.c_int, [_vp, C.c_int, _f32]),
     'p2s_model_last_guard_count': (C.c_int, [_vp, C.POINTER(_i64)]),
+    'p2s_model_set_debug_aux': (C.c_int, [_vp, _vp]),
+    'p2s_profile_enable': (C.c_int, [_vp, C.c_int]),
+    'p2s_profile_get': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)]),
     'p2s_forward_dev': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'p2s_forward_host': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     'p2s_sdf_from_logits_dev': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -201,6 +201,7 @@ int p2s_model_set_precision(p2s_model* mm, int precision, float guard_band) {
         Model* m = reinterpret_cast<Model*>(mm);
         m->precision = precision;
         m->guard_band = guard_band;
+        m->last_guard_count = 0;
     });
 }
 
@@ -209,8 +210,33 @@ int p2s_model_last_guard_count(p2s_model* mm, int64_t* count) {
         P2S_CHECK(mm && count, "null argument");
         Model* m = reinterpret_cast<Model*>(mm);
         P2S_CUDA(cudaSetDevice(m->device));
-        P2S_CUDA(cudaDeviceSynchronize());
-        P2S_CUDA(cudaMemcpy(count, m->guard_count_dev, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        *count = m->last_guard_count;
+        m->last_guard_count = 0;
+    });
+}
+
+int p2s_model_set_debug_aux(p2s_model* mm, float* aux) {
+    return guarded([&] {
+        P2S_CHECK(mm, "null model");
+        reinterpret_cast<Model*>(mm)->debug_aux = aux;
+    });
+}
+
+int p2s_profile_enable(p2s_model* mm, int on) {
+    return guarded([&] {
+        P2S_CHECK(mm, "null model");
+        Model* m = reinterpret_cast<Model*>(mm);
+        P2S_CUDA(cudaSetDevice(m->device));
+        tc_profile_reset(*m, on != 0);
+    });
+}
+
+int p2s_profile_get(p2s_model* mm, double* ms, int64_t* launches, double* flops) {
+    return guarded([&] {
+        P2S_CHECK(mm && ms && launches && flops, "null argument");
+        Model* m = reinterpret_cast<Model*>(mm);
+        P2S_CUDA(cudaSetDevice(m->device));
+        tc_profile_get(*m, ms, launches, flops);
     });
 }
 

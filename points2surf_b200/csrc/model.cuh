@@ -44,7 +44,10 @@ struct Model {
     DevBuf ws_host;                      // device staging of host-call inputs/outputs
     int64_t* guard_count_dev = nullptr;
     int64_t last_guard_count = 0;
+    float* debug_aux = nullptr;          // optional [B][kAuxStride]: R(9), feat_local_max(1024), feat_global_max(1024)
 };
+constexpr int kAuxStride = 2064;
+void debug_aux_copy(Model& m, int64_t b0, int64_t Bc, const float* R, const float* fl, const float* fg, cudaStream_t st);
 
 // net_fp32.cu
 void forward_fp32(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
@@ -52,6 +55,8 @@ void forward_fp32(Model& m, const float* patch, const float* sub, const float* q
 // net_tc.cu
 void tc_build(Model& m);
 void tc_destroy(Model& m);
+void tc_profile_reset(Model& m, bool on);
+void tc_profile_get(Model& m, double* ms, int64_t* launches, double* flops);
 void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
                 float* logits, cudaStream_t st);
 // dispatch (api.cu)

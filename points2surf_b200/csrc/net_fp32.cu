@@ -130,6 +130,22 @@ __global__ void fill_kernel(float* p, int64_t n, float v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+__global__ void debug_aux_kernel(float* aux, int64_t b0, int64_t Bc, const float* R, const float* fl, const float* fg) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Bc * kAuxStride) return;
+    int64_t b = e / kAuxStride;
+    int j = (int)(e % kAuxStride);
+    float v = 0.f;
+    if (j < 9) v = R ? R[b * 9 + j] : (j % 4 == 0 ? 1.f : 0.f);
+    else if (j < 9 + 1024) v = fl[b * 1024 + (j - 9)];
+    else if (j < 9 + 2048) v = fg[b * 1024 + (j - 9 - 1024)];
+    aux[(b0 + b) * kAuxStride + j] = v;
+}
+void debug_aux_copy(Model& m, int64_t b0, int64_t Bc, const float* R, const float* fl, const float* fg, cudaStream_t st) {
+    if (!m.debug_aux || Bc <= 0) return;
+    P2S_LAUNCH(debug_aux_kernel, (unsigned)cdiv(Bc * kAuxStride, 256), 256, 0, st, m.debug_aux, b0, Bc, R, fl, fg);
+}
+
 void launch_fill(float* p, int64_t n, float v, cudaStream_t st) {
     if (n <= 0) return;
     P2S_LAUNCH(fill_kernel, (unsigned)cdiv(n, 256), 256, 0, st, p, n, v);
@@ -300,6 +316,7 @@ void forward_fp32(Model& m, const float* patch, const float* sub, const float* q
         }
         feat(m.global, w.sub_r, Bc, S, w, w.fb_global, st);
         feat(m.local, w.patch_r, Bc, P, w, w.fb_local, st);
+        debug_aux_copy(m, b0, Bc, (m.shared_qstn || m.global.has_qstn) ? w.R : nullptr, w.fb_local, w.fb_global, st);
         // cat(local, global) after fc1_* + ReLU  (model.py:335,343,346)
         launch_gemm_nt(w.fb_local, 0, 1024, m.fc1_local.W, 0, m.fc1_local.b, w.cat, 0, 1024, (int)Bc, 512, 1024, 1, true, st);
         launch_gemm_nt(w.fb_global, 0, 1024, m.fc1_global.W, 0, m.fc1_global.b, w.cat + 512, 0, 1024, (int)Bc, 512, 1024, 1, true, st);

@@ -1,10 +1,664 @@
-// placeholder replaced by the tcgen05 implementation
+// Tensor-core implementation of PointsToSurfModel.forward (source/points_to_surf_model.py:296-352) for sm_100a.
+//
+// The per-point Conv1d(k=1) stacks (98 % of the FLOPs) run as tcgen05.mma tiles with fp16
+// operands / fp32 accumulation in TMEM; the three dependent max-reductions of the vanilla network become three
+// launches of ONE kernel (`pointnet_pass_kernel`):
+//   pass A  QSTN        : x(1300 pts) -> 64 (fp32 FMA) -> 128 -> 1024, max          (model.py:100-107)
+//   pass B  STN64       : x -> 64 -> 64 | 64 -> 128 -> 1024, max                     (model.py:190-191,41-48)
+//   pass C  final       : x -> 64 -> 64 | (W1*T) 64 -> 128 -> 1024 (no ReLU), max    (model.py:190-212)
+// The quaternion rotation is folded into the first layer's weights per query (W0*R), the 64x64 feature
+// transform into conv1's weights per query (W1*T), both exactly as in the fp32 path up to operation order.
+//
+// Tile = 128 points of one query (segments are padded with a duplicate of their first point: max-invariant).
+// Mid layers: M = 128 points (TMEM lanes), A operand = activations in TMEM (tcgen05.st by the epilogue
+// warps), B operand = weights in smem.  Big layer 128 -> 1024: M = 128 channels, A = resident W3 tile in smem,
+// B = the tile's 128-channel activations in smem, D[channel lane][point column] so that the max over points is
+// a per-thread reduction over TMEM columns (no shuffles).  Each CTA owns 512 of the 1024 channels (its half
+// of W3, 128 KB fp16, stays resident in shared memory); CTA 2j and 2j+1 stream the same queries.
+//
+// Warp roles (288 threads): warps 0-3 first layer + mid-layer epilogues (thread = point = TMEM lane),
+// warps 4-7 column-max epilogue of the big layer, warp 8 lane 0 issues every tcgen05.mma and bulk copy.
+//
+// The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
 #include "model.cuh"
+#include "tc_ptx.cuh"
+
+#ifndef P2S_TC_BOUNDED_WAIT
+#define P2S_TC_BOUNDED_WAIT 1   // trap instead of hanging if a barrier protocol bug slips in
+#endif
+
 namespace p2s {
-struct TcWeights {};
-void tc_build(Model&) {}
-void tc_destroy(Model&) {}
-void forward_tc(Model&, const float*, const float*, const float*, int64_t, float*, cudaStream_t) {
-    throw Error("tensor-core path not built yet");
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kThreads = 288;
+// shared memory map (bytes)
+constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
+constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
+constexpr uint32_t kAct2Bytes = 32768;                   // 128 points x 128 channels fp16
+constexpr uint32_t kOffW3 = 0;
+constexpr uint32_t kOffMid = kOffW3 + kW3Bytes;
+constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
+constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;
+constexpr uint32_t kSmallBytes = 64 * 4 * 4 + 256 * 4 + 128;  // Wq[64][4] fp32, mid biases[256] fp32, barriers
+constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+// TMEM map (columns)
+constexpr uint32_t kColD3 = 0;      // 2 stages x 128
+constexpr uint32_t kColDmid = 256;  // 128
+constexpr uint32_t kColA = 384;     // 2 x 32 (fp16 pairs, K = 64)
+
+struct Seg {
+    const float* ptr;   // [B, n, 3]
+    int n;              // real points per query
+    int tiles;          // ceil(n / 128)
+    int center;         // subtract the query point (model.py:303)
+};
+
+struct PassParams {
+    Seg seg[2];
+    const float* query;        // [B,3]
+    const float* R;            // [B,9] rotation folded into W0, or null
+    int tiles_per_query;
+    int B;
+    const float* W0;           // [64,3]
+    const float* b0;           // [64]
+    int num_mid;               // 1 or 3
+    int mid_N[3];              // output channels of each mid layer
+    const uint8_t* mid_img[3]; // packed fp16 operand images (K-major, LBO 128, SBO 1024)
+    const float* mid_bias[3];
+    int perq_layer;            // index of the mid layer with per-query weights, or -1
+    const uint8_t* perq_img;   // [B] x 8192 B
+    const uint8_t* w3_img;     // [2 halves][4 chunks][32768 B]  (K-major, LBO 128, SBO 2048)
+    float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer)
+};
+
+struct Bars {
+    uint64_t w_full, wq_full, a_ready, dmid_ready;
+    uint64_t act2_full[2], act2_empty[2], d3_full[2], d3_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+#if P2S_TC_BOUNDED_WAIT
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) {
+            printf("p2s: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
+            __trap();
+        }
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
 }
+
+__device__ __forceinline__ uint32_t pack_relu_bias(float a, float b, float ba, float bb) {
+    a = fmaxf(a + ba, 0.f);
+    b = fmaxf(b + bb, 0.f);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [64][4]: W0*R row, bias
+    float* s_bias = s_wq + 256;                                           // [256]: mid biases back to back
+    Bars* bars = reinterpret_cast<Bars*>(s_bias + 256);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = blockIdx.x & 1;
+    const int stream = blockIdx.x >> 1, nstreams = gridDim.x >> 1;
+    const int nq = (p.B > stream) ? (p.B - stream + nstreams - 1) / nstreams : 0;   // queries of this CTA
+    const int ntiles = nq * p.tiles_per_query;
+
+    if (tid == 0) {
+        mbar_init(&bars->w_full, 1);
+        mbar_init(&bars->wq_full, 1);
+        mbar_init(&bars->a_ready, 128);
+        mbar_init(&bars->dmid_ready, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->act2_full[i], 128);
+            mbar_init(&bars->act2_empty[i], 1);
+            mbar_init(&bars->d3_full[i], 1);
+            mbar_init(&bars->d3_empty[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
+    // mid biases -> smem
+    {
+        int off = 0;
+        for (int l = 0; l < p.num_mid; ++l) {
+            for (int i = tid; i < p.mid_N[l]; i += kThreads) s_bias[off + i] = p.mid_bias[l][i];
+            off += p.mid_N[l];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 8) {
+        // =============================================================== MMA / copy issuer (one thread)
+        if (lane == 0 && ntiles > 0) {
+            // resident weights: this CTA's half of W3 and the shared mid-layer weights
+            uint32_t bytes = kW3Bytes;
+            uint32_t mid_off[3] = {0, 0, 0};
+            {
+                uint32_t o = 0;
+                for (int l = 0; l < p.num_mid; ++l) { mid_off[l] = o; o += (uint32_t)p.mid_N[l] * 128u; }
+                for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u;
+            }
+            mbar_arrive_expect_tx(&bars->w_full, bytes);
+            for (int c = 0; c < 4; ++c)
+                bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
+            for (int l = 0; l < p.num_mid; ++l)
+                if (l != p.perq_layer) bulk_g2s(smem + kOffMid + mid_off[l], p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
+            uint32_t wq_uses = 0;
+            if (p.perq_layer >= 0) {
+                mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                bulk_g2s(smem + kOffMid + mid_off[p.perq_layer], p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
+            }
+            wait_bar(&bars->w_full, 0);
+
+            const uint32_t idesc_l3 = make_idesc_f16(128, 128);
+            const uint32_t s_w3 = smem_u32(smem + kOffW3), s_mid = smem_u32(smem + kOffMid), s_act2 = smem_u32(smem + kOffAct2);
+            int it_mid = 0, l_mid = 0;          // next mid MMA to issue: tile, layer
+            int it_l3 = 0, c_l3 = 0;            // next big-layer chunk to issue
+            while (it_l3 < ntiles) {
+                bool progress = false;
+                // ---- mid layer (priority: it unblocks the epilogue chain)
+                if (it_mid < ntiles) {
+                    const uint32_t round = (uint32_t)(it_mid * p.num_mid + l_mid);
+                    if (mbar_try_wait(&bars->a_ready, round & 1)) {
+                        tc_fence_after();
+                        const int tq = it_mid % p.tiles_per_query;
+                        if (l_mid == p.perq_layer && tq == 0) { wait_bar(&bars->wq_full, wq_uses & 1); ++wq_uses; }
+                        const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l_mid]);
+                        const uint32_t a_t = tmem + kColA + (uint32_t)(l_mid & 1) * 32u;
+                        const uint32_t b_s = s_mid + mid_off[l_mid];
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(tmem + kColDmid, a_t + ks * 8, make_smem_desc(b_s + ks * 256, 128, 1024), idesc, ks > 0);
+                        mma_commit(&bars->dmid_ready);
+                        // the per-query layer's MMA of the query's last tile is complete once the NEXT layer's
+                        // input is ready: prefetch the next query's weights then
+                        if (p.perq_layer >= 0 && l_mid == p.perq_layer + 1 && tq == p.tiles_per_query - 1) {
+                            const int qn = it_mid / p.tiles_per_query + 1;
+                            if (qn < nq) {
+                                mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                                bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
+                                         p.perq_img + ((size_t)stream + (size_t)qn * nstreams) * 8192, 8192, &bars->wq_full);
+                            }
+                        }
+                        if (++l_mid == p.num_mid) { l_mid = 0; ++it_mid; }
+                        progress = true;
+                    }
+                }
+                // ---- big layer chunk
+                if (it_l3 < ntiles) {
+                    const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
+                    const uint32_t stage = g & 1, use = g >> 1;
+                    const uint32_t buf = (uint32_t)it_l3 & 1, buse = (uint32_t)it_l3 >> 1;
+                    bool ok = mbar_try_wait(&bars->d3_empty[stage], (use & 1) ^ 1);
+                    if (ok && c_l3 == 0) ok = mbar_try_wait(&bars->act2_full[buf], buse & 1);
+                    if (ok) {
+                        tc_fence_after();
+                        const uint32_t a_s = s_w3 + (uint32_t)c_l3 * 32768u, b_s = s_act2 + buf * kAct2Bytes;
+                        const uint32_t d = tmem + kColD3 + stage * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(d, make_smem_desc(a_s + ks * 256, 128, 2048), make_smem_desc(b_s + ks * 256, 128, 2048), idesc_l3, ks > 0);
+                        mma_commit(&bars->d3_full[stage]);
+                        if (++c_l3 == 4) { mma_commit(&bars->act2_empty[buf]); c_l3 = 0; ++it_l3; }
+                        progress = true;
+                    }
+                }
+                (void)progress;
+            }
+        }
+    } else if (warp < 4) {
+        // =============================================================== first layer + mid-layer epilogues
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        int it = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q = stream + qi * nstreams;
+            // W0 * R (+ bias) for this query -> smem
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // previous query's readers are done
+            if (tid < 64) {
+                float w0 = p.W0[tid * 3 + 0], w1 = p.W0[tid * 3 + 1], w2 = p.W0[tid * 3 + 2];
+                float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+                if (p.R) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) r[i] = p.R[(size_t)q * 9 + i];
+                }
+                s_wq[tid * 4 + 0] = w0 * r[0] + w1 * r[3] + w2 * r[6];
+                s_wq[tid * 4 + 1] = w0 * r[1] + w1 * r[4] + w2 * r[7];
+                s_wq[tid * 4 + 2] = w0 * r[2] + w1 * r[5] + w2 * r[8];
+                s_wq[tid * 4 + 3] = p.b0[tid];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float qx = p.query[(size_t)q * 3 + 0], qy = p.query[(size_t)q * 3 + 1], qz = p.query[(size_t)q * 3 + 2];
+            for (int tq = 0; tq < p.tiles_per_query; ++tq, ++it) {
+                // ---- gather this thread's point
+                const int sgi = tq < p.seg[0].tiles ? 0 : 1;
+                const Seg& sg = p.seg[sgi];
+                int local = (tq - (sgi ? p.seg[0].tiles : 0)) * kTile + tid;
+                if (local >= sg.n) local = 0;                              // duplicate padding
+                const float* src = sg.ptr + ((size_t)q * sg.n + local) * 3;
+                float x = src[0], y = src[1], z = src[2];
+                if (sg.center) { x -= qx; y -= qy; z -= qz; }
+                // ---- layer 0 (fp32 FMA): 3 -> 64, ReLU, pack to fp16 pairs, store as the A operand in TMEM
+                {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 wa = *reinterpret_cast<const float4*>(s_wq + (2 * j) * 4);
+                        const float4 wb = *reinterpret_cast<const float4*>(s_wq + (2 * j + 1) * 4);
+                        float ha = fmaf(wa.x, x, fmaf(wa.y, y, fmaf(wa.z, z, wa.w)));
+                        float hb = fmaf(wb.x, x, fmaf(wb.y, y, fmaf(wb.z, z, wb.w)));
+                        v[j] = pack_relu_bias(ha, hb, 0.f, 0.f);
+                    }
+                    tmem_st_x32(tmem + lane_base + kColA, v);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->a_ready);
+                }
+                // ---- mid layers
+                int boff = 0;
+                for (int l = 0; l < p.num_mid; ++l) {
+                    const uint32_t round = (uint32_t)(it * p.num_mid + l);
+                    wait_bar(&bars->dmid_ready, round & 1);
+                    tc_fence_after();
+                    const int N = p.mid_N[l];
+                    const bool last = (l == p.num_mid - 1);
+                    uint32_t buf = 0;
+                    if (last) {
+                        buf = (uint32_t)it & 1;
+                        wait_bar(&bars->act2_empty[buf], (((uint32_t)it >> 1) & 1) ^ 1);
+                    }
+                    for (int n0 = 0; n0 < N; n0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_x32(tmem + lane_base + kColDmid + n0, r);
+                        tmem_ld_wait();
+                        uint32_t v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = pack_relu_bias(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]),
+                                                  s_bias[boff + n0 + 2 * j], s_bias[boff + n0 + 2 * j + 1]);
+                        if (!last) {
+                            // next layer's A operand: K index = channel; columns hold channel pairs
+                            uint32_t w[8];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) w[j] = v[h * 8 + j];
+                                tmem_st_x8(tmem + lane_base + kColA + (uint32_t)((l + 1) & 1) * 32u + (uint32_t)(n0 / 2 + h * 8), w);
+                            }
+                        } else {
+                            // big layer's B operand [point row][channel K] K-major, LBO 128, SBO 2048
+                            uint8_t* dst = smem + kOffAct2 + buf * kAct2Bytes + (uint32_t)(tid >> 3) * 2048u + (uint32_t)(tid & 7) * 16u;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(dst + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    }
+                    if (!last) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(&bars->a_ready);
+                    } else {
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&bars->act2_full[buf]);
+                    }
+                    boff += N;
+                }
+            }
+        }
+    } else {
+        // =============================================================== big-layer epilogue: max over the tile's points
+        const int ew = warp - 4;
+        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        const int ch_lane = ew * 32 + lane;
+        int it = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q = stream + qi * nstreams;
+            float acc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int tq = 0; tq < p.tiles_per_query; ++tq, ++it) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t g = (uint32_t)(it * 4 + c);
+                    const uint32_t stage = g & 1, use = g >> 1;
+                    wait_bar(&bars->d3_full[stage], use & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + lane_base + kColD3 + stage * 128u;
+                    float m = acc[c];
+#pragma unroll
+                    for (int n0 = 0; n0 < 128; n0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld_x32(d + n0, r0);
+                        tmem_ld_x32(d + n0 + 32, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+                    }
+                    acc[c] = m;
+                    tc_fence_before();
+                    mbar_arrive(&bars->d3_empty[stage]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p.out[(size_t)q * 1024 + half * 512 + c * 128 + ch_lane] = acc[c];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (device side, once per model)
+// ------------------------------------------------------------------------------------------------
+// fp32 W[rows][K] -> fp16 K-major no-swizzle operand image: (r/8)*sbo + (k/8)*128 + (r%8)*16 + (k%8)*2
+__global__ void pack_kmajor_kernel(const float* __restrict__ W, int rows, int K, int row0, uint32_t sbo, uint8_t* __restrict__ img) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * K) return;
+    int r = e / K, k = e % K;
+    uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__half*>(img + off) = __float2half_rn(W[(size_t)(row0 + r) * K + k]);
+}
+
+// per-query W1*T (fp32 [B][64][64], row = output channel) -> fp16 images of 8192 B
+__global__ void pack_perq_kernel(const float* __restrict__ W, int64_t B, uint8_t* __restrict__ img) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * 4096) return;
+    int64_t b = e >> 12;
+    int r = (int)((e >> 6) & 63), k = (int)(e & 63);
+    uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__half*>(img + b * 8192 + off) = __float2half_rn(W[e]);
+}
+
+// out[b][i][j] = in[b][j][i] for 64x64 blocks (the STN's transform, transposed for the W1*T product)
+__global__ void transpose64_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * 4096) return;
+    int64_t b = e >> 12;
+    int i = (int)((e >> 6) & 63), j = (int)(e & 63);
+    out[e] = in[b * 4096 + j * 64 + i];
+}
+
+__global__ void guard_flag_kernel(const float* __restrict__ logits, int64_t B, float band, int32_t* __restrict__ list, int* __restrict__ count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (fabsf(logits[i * 2 + 1]) < band) list[atomicAdd(count, 1)] = (int32_t)i;
+}
+__global__ void guard_gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ list, int n, int row_floats, float* __restrict__ dst) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * row_floats) return;
+    int i = (int)(e / row_floats), j = (int)(e % row_floats);
+    dst[e] = src[(int64_t)list[i] * row_floats + j];
+}
+__global__ void guard_scatter_kernel(const float* __restrict__ src, const int32_t* __restrict__ list, int n, float* __restrict__ logits) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    logits[(int64_t)list[i] * 2 + 0] = src[i * 2 + 0];
+    logits[(int64_t)list[i] * 2 + 1] = src[i * 2 + 1];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct TcStack {           // one conv stack ending in the 128 -> 1024 layer
+    uint8_t* w3_img = nullptr;     // 2 x 4 x 32768
+    uint8_t* mid_img[3] = {nullptr, nullptr, nullptr};
+    const float* mid_bias[3] = {nullptr, nullptr, nullptr};
+    int mid_N[3] = {0, 0, 0};
+    int num_mid = 0;
+    const float* W0 = nullptr;
+    const float* b0 = nullptr;
+    const float* b3 = nullptr;
+};
+
+struct TcWeights {
+    TcStack qstn;                // pass A
+    TcStack stn[2], fin[2];      // [0] local, [1] global: pass B, pass C
+    std::vector<void*> allocs;
+    int sm_count = 148;
+    // profile of the dominant kernel (bench.py roofline)
+    bool prof_on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    double prof_flops = 0.0;
+    ~TcWeights() {
+        for (void* a : allocs) cudaFree(a);
+        for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+};
+
+namespace {
+
+uint8_t* tc_alloc(TcWeights& t, size_t bytes) {
+    void* p = nullptr;
+    P2S_CUDA(cudaMalloc(&p, bytes));
+    P2S_CUDA(cudaMemset(p, 0, bytes));
+    t.allocs.push_back(p);
+    return (uint8_t*)p;
+}
+
+uint8_t* pack_layer(TcWeights& t, const Layer& L, uint32_t sbo) {   // whole layer as one image
+    uint8_t* img = tc_alloc(t, (size_t)L.cout * L.cin * 2);
+    P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, 0, sbo, img);
+    return img;
+}
+
+uint8_t* pack_w3(TcWeights& t, const Layer& L) {   // 8 chunks of 128 rows, each its own 32 KB image
+    P2S_CHECK(L.cout == 1024 && L.cin == 128, "big layer must be 128 -> 1024");
+    uint8_t* img = tc_alloc(t, 8 * 32768);
+    for (int c = 0; c < 8; ++c)
+        P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv(128 * 128, 256), 256, 0, 0, L.W, 128, 128, c * 128, 2048u, img + (size_t)c * 32768);
+    return img;
+}
+
+void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const float* query, const float* R,
+                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st) {
+    PassParams p{};
+    p.seg[0] = s0; p.seg[1] = s1;
+    p.query = query; p.R = R;
+    p.tiles_per_query = s0.tiles + s1.tiles;
+    p.B = (int)B;
+    p.W0 = s.W0; p.b0 = s.b0;
+    p.num_mid = s.num_mid;
+    for (int l = 0; l < 3; ++l) { p.mid_N[l] = s.mid_N[l]; p.mid_img[l] = s.mid_img[l]; p.mid_bias[l] = s.mid_bias[l]; }
+    p.perq_layer = perq_layer;
+    p.perq_img = perq_img;
+    p.w3_img = s.w3_img;
+    p.out = out;
+    TcWeights& t = *m.tc;
+    int grid = 2 * (t.sm_count / 2);
+    if ((int64_t)grid / 2 > B) grid = (int)(2 * B);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (t.prof_on) {
+        P2S_CUDA(cudaEventCreate(&e0)); P2S_CUDA(cudaEventCreate(&e1));
+        P2S_CUDA(cudaEventRecord(e0, st));
+    }
+    P2S_LAUNCH(pointnet_pass_kernel, grid, kThreads, kSmemBytes, st, p);
+    if (t.prof_on) {
+        P2S_CUDA(cudaEventRecord(e1, st));
+        t.prof_events.emplace_back(e0, e1);
+        // algorithmic FLOPs of this launch: real (un-padded) points, un-duplicated layers
+        double mac_pt = 3.0 * 64 + 128.0 * 1024;
+        int prev = 64;
+        for (int l = 0; l < s.num_mid; ++l) { mac_pt += (double)prev * s.mid_N[l]; prev = s.mid_N[l]; }
+        t.prof_flops += 2.0 * mac_pt * (double)(s0.n + s1.n) * (double)B;
+    }
+}
+
+Seg make_seg(const float* ptr, int n, int center) { return Seg{ptr, n, n > 0 ? (n + kTile - 1) / kTile : 0, center}; }
+
+void fc_tail(const Layer& b3src, const Stn& s, const float* gmax_raw, int64_t Bc, float* g, float* f1, float* f2, float* out, cudaStream_t st) {
+    // g = relu(max + b3) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
+    P2S_CUDA(cudaMemcpyAsync(g, gmax_raw, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
+    launch_bias_act(g, b3src.b, Bc, 1024, true, st);
+    launch_gemm_nt(g, 0, 1024, s.fc1.W, 0, s.fc1.b, f1, 0, 512, (int)Bc, 512, 1024, 1, true, st);
+    launch_gemm_nt(f1, 0, 512, s.fc2.W, 0, s.fc2.b, f2, 0, 256, (int)Bc, 256, 512, 1, true, st);
+    launch_gemm_nt(f2, 0, 256, s.fc3.W, 0, s.fc3.b, out, 0, s.fc3.cout, (int)Bc, s.fc3.cout, 256, 1, false, st);
+}
+
+}  // namespace
+
+void tc_build(Model& m) {
+    P2S_CHECK(m.cfg.net_size == 1024, "tensor-core path needs net_size 1024");
+    TcWeights* t = new TcWeights();
+    m.tc = t;
+    cudaDeviceProp prop;
+    P2S_CUDA(cudaGetDeviceProperties(&prop, m.device));
+    t->sm_count = prop.multiProcessorCount;
+    P2S_CUDA(cudaFuncSetAttribute(pointnet_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    auto build_stn = [&](TcStack& s, const Stn& stn, const Layer* c0a, const Layer* c0b) {
+        // QSTN: x -> conv1(3->64) [layer 0] -> conv2 (64->128) -> conv3 ; STN64 on feat: conv0a [layer 0] -> conv0b -> conv1 -> conv2 -> conv3
+        if (!c0a) {
+            s.W0 = stn.c1.W; s.b0 = stn.c1.b;
+            s.num_mid = 1;
+            s.mid_img[0] = pack_layer(*t, stn.c2, 1024); s.mid_bias[0] = stn.c2.b; s.mid_N[0] = 128;
+        } else {
+            s.W0 = c0a->W; s.b0 = c0a->b;
+            s.num_mid = 3;
+            s.mid_img[0] = pack_layer(*t, *c0b, 1024); s.mid_bias[0] = c0b->b; s.mid_N[0] = 64;
+            s.mid_img[1] = pack_layer(*t, stn.c1, 1024); s.mid_bias[1] = stn.c1.b; s.mid_N[1] = 64;
+            s.mid_img[2] = pack_layer(*t, stn.c2, 1024); s.mid_bias[2] = stn.c2.b; s.mid_N[2] = 128;
+        }
+        s.w3_img = pack_w3(*t, stn.c3);
+        s.b3 = stn.c3.b;
+    };
+    auto build_fin = [&](TcStack& s, const Feat& f) {
+        s.W0 = f.conv0a.W; s.b0 = f.conv0a.b;
+        s.num_mid = 3;
+        s.mid_img[0] = pack_layer(*t, f.conv0b, 1024); s.mid_bias[0] = f.conv0b.b; s.mid_N[0] = 64;
+        s.mid_img[1] = nullptr; s.mid_bias[1] = f.conv1.b; s.mid_N[1] = 64;       // per query: conv1 * T
+        s.mid_img[2] = pack_layer(*t, f.conv2, 1024); s.mid_bias[2] = f.conv2.b; s.mid_N[2] = 128;
+        s.w3_img = pack_w3(*t, f.conv3);
+        s.b3 = f.conv3.b;
+    };
+    if (m.shared_qstn) build_stn(t->qstn, m.point_stn, nullptr, nullptr);
+    else if (m.global.has_qstn) build_stn(t->qstn, m.global.stn1, nullptr, nullptr);
+    build_stn(t->stn[0], m.local.stn2, &m.local.conv0a, &m.local.conv0b);
+    build_stn(t->stn[1], m.global.stn2, &m.global.conv0a, &m.global.conv0b);
+    build_fin(t->fin[0], m.local);
+    build_fin(t->fin[1], m.global);
+    P2S_CUDA(cudaDeviceSynchronize());
+}
+
+void tc_destroy(Model& m) {
+    delete m.tc;
+    m.tc = nullptr;
+}
+
+void tc_profile_reset(Model& m, bool on) {
+    TcWeights& t = *m.tc;
+    for (auto& e : t.prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    t.prof_events.clear();
+    t.prof_flops = 0.0;
+    t.prof_on = on;
+}
+
+void tc_profile_get(Model& m, double* ms, int64_t* launches, double* flops) {
+    TcWeights& t = *m.tc;
+    double total = 0.0;
+    for (auto& e : t.prof_events) {
+        P2S_CUDA(cudaEventSynchronize(e.second));
+        float x = 0.f;
+        P2S_CUDA(cudaEventElapsedTime(&x, e.first, e.second));
+        total += x;
+    }
+    *ms = total;
+    *launches = (int64_t)t.prof_events.size();
+    *flops = t.prof_flops;
+}
+
+void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+                float* logits, cudaStream_t st) {
+    TcWeights& t = *m.tc;
+    const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
+    const int64_t Bc_max = 8192;
+    // workspace (floats per query)
+    const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 2048 /* 8 KB perq image */ + 16;
+    float* base = m.ws_net.as<float>(per_q * (size_t)Bc_max + 1024);
+    float* pcur = base;
+    auto take = [&](size_t n) { float* r = pcur; pcur += (n * (size_t)Bc_max + 63) / 64 * 64; return r; };
+    float* gmax = take(1024); float* g = take(1024); float* f1 = take(512); float* f2 = take(256);
+    float* q4 = take(4); float* R = take(9); float* T = take(4096); float* Tt = take(4096);
+    float* fmax_l = take(1024); float* fmax_g = take(1024); float* cat = take(1024); float* h3 = take(256); float* h4 = take(128);
+    uint8_t* perq = reinterpret_cast<uint8_t*>(take(2048));
+
+    for (int64_t b0 = 0; b0 < B; b0 += Bc_max) {
+        const int64_t Bc = (B - b0 < Bc_max) ? (B - b0) : Bc_max;
+        const float* pa = patch + b0 * P * 3;
+        const float* su = sub + b0 * S * 3;
+        const float* qu = query + b0 * 3;
+        const float* Rq = nullptr;
+        if (m.shared_qstn) {
+            // pass A over cat(patch, sub - q)   (model.py:303,325-327)
+            launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st);
+            fc_tail(m.point_stn.c3, m.point_stn, gmax, Bc, g, f1, f2, q4, st);
+            launch_quat_to_rot(q4, R, Bc, st);
+            Rq = R;
+        } else if (m.global.has_qstn) {
+            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st);
+            fc_tail(m.global.stn1.c3, m.global.stn1, gmax, Bc, g, f1, f2, q4, st);
+            launch_quat_to_rot(q4, R, Bc, st);
+            Rq = R;
+        }
+        for (int br = 1; br >= 0; --br) {    // global first like the reference, then local
+            const Feat& f = br ? m.global : m.local;
+            const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
+            float* fmax = br ? fmax_g : fmax_l;
+            // pass B: STN64 -> T
+            launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st);
+            fc_tail(f.stn2.c3, f.stn2, gmax, Bc, g, f1, f2, T, st);
+            launch_add_identity64(T, Bc, st);
+            // W1' = conv1.W * T  -> per-query fp16 operand images
+            P2S_LAUNCH(transpose64_kernel, (unsigned)cdiv(Bc * 4096, 256), 256, 0, st, T, Tt, Bc);
+            launch_gemm_nt(f.conv1.W, 0, 64, Tt, 4096, nullptr, T, 4096, 64, 64, 64, 64, (int)Bc, false, st);
+            P2S_LAUNCH(pack_perq_kernel, (unsigned)cdiv(Bc * 4096, 256), 256, 0, st, T, Bc, perq);
+            // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
+            launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st);
+            launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
+        }
+        debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
+        launch_gemm_nt(fmax_l, 0, 1024, m.fc1_local.W, 0, m.fc1_local.b, cat, 0, 1024, (int)Bc, 512, 1024, 1, true, st);
+        launch_gemm_nt(fmax_g, 0, 1024, m.fc1_global.W, 0, m.fc1_global.b, cat + 512, 0, 1024, (int)Bc, 512, 1024, 1, true, st);
+        launch_gemm_nt(cat, 0, 1024, m.fc2.W, 0, m.fc2.b, h3, 0, 256, (int)Bc, 256, 1024, 1, true, st);
+        launch_gemm_nt(h3, 0, 256, m.fc3.W, 0, m.fc3.b, h4, 0, 128, (int)Bc, 128, 256, 1, true, st);
+        launch_gemm_nt(h4, 0, 128, m.fc4.W, 0, m.fc4.b, logits + b0 * 2, 0, 2, (int)Bc, 2, 128, 1, false, st);
+    }
+
+    // guard band: queries whose sign logit is too close to 0 for fp16-operand arithmetic are recomputed in fp32
+    if (m.guard_band > 0.f) {
+        int32_t* list = m.ws_guard.as<int32_t>((size_t)B + 64);
+        int* count = reinterpret_cast<int*>(list + B);
+        P2S_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+        P2S_LAUNCH(guard_flag_kernel, (unsigned)cdiv(B, 256), 256, 0, st, logits, B, m.guard_band, list, count);
+        int n = 0;
+        P2S_CUDA(cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        P2S_CUDA(cudaStreamSynchronize(st));
+        m.last_guard_count += n;
+        if (n > 0) {
+            const size_t rowp = (size_t)P * 3, rows = (size_t)S * 3;
+            float* gbuf = m.ws_misc.as<float>((size_t)n * (rowp + rows + 3 + 2) + 64);
+            float* gp = gbuf; float* gs = gp + (size_t)n * rowp; float* gq = gs + (size_t)n * rows; float* gl = gq + ((size_t)n * 3 + 3) / 4 * 4;
+            P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * rowp, 256), 256, 0, st, patch, list, n, (int)rowp, gp);
+            P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * rows, 256), 256, 0, st, sub, list, n, (int)rows, gs);
+            P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * 3, 256), 256, 0, st, query, list, n, 3, gq);
+            forward_fp32(m, gp, gs, gq, n, gl, st);
+            P2S_LAUNCH(guard_scatter_kernel, (unsigned)cdiv(n, 256), 256, 0, st, gl, list, n, logits);
+        }
+    }
+}
+
 }  // namespace p2s

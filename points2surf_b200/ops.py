@@ -64,6 +64,26 @@ class Engine:
         except Exception:
             pass
 
+    def forward_with_aux(self, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms):
+        """-> (logits, dict(trans [B,3,3], feat_local_max [B,1024], feat_global_max [B,1024])) -- parity diagnostics."""
+        B = patch_pts_ps.shape[0]
+        aux = torch.zeros((B, 2064), dtype=torch.float32, device=patch_pts_ps.device)
+        check(self.lib.p2s_model_set_debug_aux(self.handle, _ptr(aux)))
+        try:
+            out = self.forward(patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms)
+            torch.cuda.synchronize()
+        finally:
+            check(self.lib.p2s_model_set_debug_aux(self.handle, None))
+        return out, {'trans': aux[:, :9].reshape(B, 3, 3), 'feat_local_max': aux[:, 9:1033], 'feat_global_max': aux[:, 1033:2057]}
+
+    def profile_enable(self, on=True):
+        check(self.lib.p2s_profile_enable(self.handle, int(bool(on))))
+
+    def profile_get(self):
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        check(self.lib.p2s_profile_get(self.handle, C.byref(ms), C.byref(n), C.byref(fl)))
+        return {'ms': ms.value, 'launches': n.value, 'flops': fl.value, 'kernel': 'pointnet_pass_kernel'}
+
     def last_guard_count(self):
         n = C.c_int64()
         check(self.lib.p2s_model_last_guard_count(self.handle, C.byref(n)))

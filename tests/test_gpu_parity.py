@@ -290,3 +290,68 @@ def test_mesh_chamfer_against_analytic_sphere():
     dd = rng.standard_normal((10000, 3))
     s_ref = 0.5 * dd / np.linalg.norm(dd, axis=1, keepdims=True)
     assert orc.chamfer(s_mesh, s_ref) / 20000 < 0.01
+
+
+# ------------------------------------------------------------------ a7 on the tensor-core path
+# fp16 operands (11-bit significand, like the TF32 the reference's cuDNN convs use on Ampere+), fp32 accumulate.
+# Tolerances (stated): max features within 2e-2 * max|feature| of the fp32 oracle; logits within
+# 3e-2 * max(1, max|logit|); with the guard band on, the sign class is exact.
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_forward_tc_matches_oracle(variant):
+    sd, inp, g = golden_model_case(variant)
+    v = synth.VARIANTS[variant]
+    eng = make_engine(sd, variant, precision='tc', guard_band=0.0)
+    args = (cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms']))
+    out, aux = eng.forward_with_aux(*args)
+    ref, raux = orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'],
+                                  v['use_point_stn'], v['shared_transformer'], return_aux=True)
+    if 'trans' in raux:
+        terr = np.abs(aux['trans'].cpu().numpy() - raux['trans']).max()
+        print('trans err', terr)
+        assert terr < 2e-2
+    for k in ('feat_global_max', 'feat_local_max'):
+        a, r = aux[k].cpu().numpy(), raux[k]
+        err = np.abs(a - r).max() / np.abs(r).max()
+        print(variant, k, 'rel err', err)
+        assert err < 2e-2, (k, err)
+    out = out.cpu().numpy()
+    err = np.abs(out - ref).max()
+    print(variant, 'logit err', err, 'scale', np.abs(ref).max())
+    assert err < 3e-2 * max(1.0, np.abs(ref).max()), err
+
+
+def test_forward_tc_guard_band_makes_signs_exact():
+    sd = calibrated_state_dict('vanilla', 21)
+    inp = synth.make_model_inputs(200, seed=5)
+    args = (cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms']))
+    eng32 = make_engine(sd, 'vanilla', precision='fp32')
+    ref = eng32.forward(*args).cpu().numpy()
+    eng = make_engine(sd, 'vanilla', precision='tc', guard_band=0.0)
+    raw = eng.forward(*args).cpu().numpy()
+    err = np.abs(raw - ref).max()
+    print('tc vs fp32 logit err', err, 'scale', np.abs(ref).max())
+    band = max(4.0 * err, 1e-3)
+    eng.set_precision('tc', guard_band=band)
+    out = eng.forward(*args).cpu().numpy()
+    n_guard = eng.last_guard_count()
+    assert ((out[:, 1] >= 0) == (ref[:, 1] >= 0)).all()
+    inside = np.abs(raw[:, 1]) < band
+    assert n_guard == int(inside.sum())
+    assert np.abs(out[inside] - ref[inside]).max() < 1e-4 if inside.any() else True
+    # ragged batch sizes through the tile scheduler (B not a multiple of the CTA count; B = 1)
+    for B in (1, 3, 75, 149):
+        o = eng.forward(args[0][:B], args[1][:B], args[2][:B]).cpu().numpy()
+        assert np.abs(o - ref[:B]).max() < max(4.0 * err, 1e-3) + 1e-4
+
+
+def test_reconstruct_tc_close_to_fp32():
+    sd = calibrated_state_dict('vanilla', 31)
+    cloud = synth.make_cloud('sphere', 3000, seed=6)
+    e32 = make_engine(sd, 'vanilla', precision='fp32')
+    etc = make_engine(sd, 'vanilla', precision='tc', guard_band=0.05)
+    lin_a, sdf_a = e32.reconstruct(cu(cloud), 16, 3, 0, 99)
+    lin_b, sdf_b = etc.reconstruct(cu(cloud), 16, 3, 0, 99)
+    assert torch.equal(lin_a, lin_b)
+    a, b = sdf_a.cpu().numpy(), sdf_b.cpu().numpy()
+    assert np.array_equal(np.sign(a), np.sign(b))
+    assert np.abs(a - b).max() < 5e-3
