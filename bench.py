@@ -268,7 +268,8 @@ def run_b200(args):
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
                         'flops_per_launch': prof['flops'] / prof['launches'], 'ms_per_launch': prof['ms'] / prof['launches'],
                         'share_of_step': prof['ms'] / dev_ms}
-        cpu = cpu_reference_rate(args, cloud, sd, args.cpu_sample, fc4_bias=fc4_bias)
+        cpu = cpu_reference_rate(args, cloud, sd, args.cpu_sample, fc4_bias=fc4_bias) if args.cpu_sample > 0 else \
+            dict(value=None, cores=os.cpu_count(), t_assemble_s=0.0, t_network_s=0.0)
         line = {
             'metric': 'SDF queries/sec at grid_res=%d' % args.grid_res, 'value': value, 'unit': 'queries/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
