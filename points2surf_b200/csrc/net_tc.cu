@@ -16,8 +16,9 @@
 // a per-thread reduction over TMEM columns (no shuffles).  Each CTA owns 512 of the 1024 channels (its half
 // of W3, 128 KB fp16, stays resident in shared memory); CTA 2j and 2j+1 stream the same queries.
 //
-// Warp roles (288 threads): warps 0-3 first layer + mid-layer epilogues (thread = point = TMEM lane),
-// warps 4-7 column-max epilogue of the big layer, warp 8 lane 0 issues every tcgen05.mma and bulk copy.
+// Warp roles (416 threads): warps 0-3 and 9-12 are two chains (even / odd tiles) doing the first layer and the
+// mid-layer epilogues (thread = point = TMEM lane), warps 4-7 the column-max epilogue of the big layer, warp 8
+// lane 0 issues every tcgen05.mma and bulk copy.
 //
 // The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
 #include "model.cuh"
@@ -34,7 +35,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kThreads = 288;
+constexpr int kThreads = 416;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 MMA issuer | 9-12 chain 1
 // shared memory map (bytes)
 constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
 constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
@@ -43,13 +44,13 @@ constexpr uint32_t kOffW3 = 0;
 constexpr uint32_t kOffMid = kOffW3 + kW3Bytes;
 constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
 constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;
-constexpr uint32_t kSmallBytes = 64 * 4 * 4 + 256 * 4 + 128;  // Wq[64][4] fp32, mid biases[256] fp32, barriers
+constexpr uint32_t kSmallBytes = 2 * 192 * 4 + 320 * 4 + 144;  // Wq[2 chains][3][64], biases[256 mid + 64 first], barriers
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM map (columns)
 constexpr uint32_t kColD3 = 0;      // 2 stages x 128
-constexpr uint32_t kColDmid = 256;  // 128
-constexpr uint32_t kColA = 384;     // 2 x 32 (fp16 pairs, K = 64)
+constexpr uint32_t kColDmid = 256;  // 128, shared by the two chains (dmid_free hand-over)
+constexpr uint32_t kColA = 384;     // 2 chains x 32 (fp16 pairs, K = 64)
 
 struct Seg {
     const float* ptr;   // [B, n, 3]
@@ -77,10 +78,12 @@ struct PassParams {
 };
 
 struct Bars {
-    uint64_t w_full, wq_full, a_ready, dmid_ready;
+    uint64_t w_full, wq_full, perq_done, dmid_free;
+    uint64_t a_ready[2], dmid_ready[2];
     uint64_t act2_full[2], act2_empty[2], d3_full[2], d3_empty[2];
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 144, "barrier block");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 #if P2S_TC_BOUNDED_WAIT
@@ -96,31 +99,33 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
-__device__ __forceinline__ uint32_t pack_relu_bias(float a, float b, float ba, float bb) {
-    a = fmaxf(a + ba, 0.f);
-    b = fmaxf(b + bb, 0.f);
+// relu(a), relu(b) -> packed fp16x2 (low half = a), saturating
+__device__ __forceinline__ uint32_t pack_relu(float a, float b) {
     uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [64][4]: W0*R row, bias
-    float* s_bias = s_wq + 256;                                           // [256]: mid biases back to back
-    Bars* bars = reinterpret_cast<Bars*>(s_bias + 256);
+    float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [2][3][64]: rows of (W0*R)^T per chain
+    float* s_bias = s_wq + 2 * 192;                                       // [256] mid biases back to back, [64] first-layer bias
+    Bars* bars = reinterpret_cast<Bars*>(s_bias + 320);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = blockIdx.x & 1;
     const int stream = blockIdx.x >> 1, nstreams = gridDim.x >> 1;
     const int nq = (p.B > stream) ? (p.B - stream + nstreams - 1) / nstreams : 0;   // queries of this CTA
-    const int ntiles = nq * p.tiles_per_query;
+    const int tpq = p.tiles_per_query;
+    const int ntiles = nq * tpq;
 
     if (tid == 0) {
         mbar_init(&bars->w_full, 1);
         mbar_init(&bars->wq_full, 1);
-        mbar_init(&bars->a_ready, 128);
-        mbar_init(&bars->dmid_ready, 1);
+        mbar_init(&bars->perq_done, 1);
+        mbar_init(&bars->dmid_free, 128);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->a_ready[i], 128);
+            mbar_init(&bars->dmid_ready[i], 1);
             mbar_init(&bars->act2_full[i], 128);
             mbar_init(&bars->act2_empty[i], 1);
             mbar_init(&bars->d3_full[i], 1);
@@ -129,13 +134,13 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         fence_mbar_init();
     }
     if (warp == 8) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
-    // mid biases -> smem
     {
         int off = 0;
         for (int l = 0; l < p.num_mid; ++l) {
             for (int i = tid; i < p.mid_N[l]; i += kThreads) s_bias[off + i] = p.mid_bias[l][i];
             off += p.mid_N[l];
         }
+        for (int i = tid; i < 64; i += kThreads) s_bias[256 + i] = p.b0[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -145,7 +150,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
     if (warp == 8) {
         // =============================================================== MMA / copy issuer (one thread)
         if (lane == 0 && ntiles > 0) {
-            // resident weights: this CTA's half of W3 and the shared mid-layer weights
             uint32_t bytes = kW3Bytes;
             uint32_t mid_off[3] = {0, 0, 0};
             {
@@ -158,49 +162,57 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
             for (int l = 0; l < p.num_mid; ++l)
                 if (l != p.perq_layer) bulk_g2s(smem + kOffMid + mid_off[l], p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
-            uint32_t wq_uses = 0;
-            if (p.perq_layer >= 0) {
+            const bool perq = p.perq_layer >= 0;
+            if (perq) {
                 mbar_arrive_expect_tx(&bars->wq_full, 8192);
                 bulk_g2s(smem + kOffMid + mid_off[p.perq_layer], p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
+                wait_bar(&bars->wq_full, 0);
             }
             wait_bar(&bars->w_full, 0);
 
             const uint32_t idesc_l3 = make_idesc_f16(128, 128);
             const uint32_t s_w3 = smem_u32(smem + kOffW3), s_mid = smem_u32(smem + kOffMid), s_act2 = smem_u32(smem + kOffAct2);
-            int it_mid = 0, l_mid = 0;          // next mid MMA to issue: tile, layer
-            int it_l3 = 0, c_l3 = 0;            // next big-layer chunk to issue
+            int it_mid[2] = {0, 1}, l_mid[2] = {0, 0};
+            uint32_t rnd[2] = {0, 0};           // per-chain (tile, layer) round counter
+            uint32_t g_mid = 0;                 // mid MMAs issued so far (D_mid hand-over)
+            int loaded_q = 0, perq_count = 0;   // per-query weights resident for local query `loaded_q`
+            bool pq_loading = false;
+            int it_l3 = 0, c_l3 = 0;
             while (it_l3 < ntiles) {
-                bool progress = false;
-                // ---- mid layer (priority: it unblocks the epilogue chain)
-                if (it_mid < ntiles) {
-                    const uint32_t round = (uint32_t)(it_mid * p.num_mid + l_mid);
-                    if (mbar_try_wait(&bars->a_ready, round & 1)) {
-                        tc_fence_after();
-                        const int tq = it_mid % p.tiles_per_query;
-                        if (l_mid == p.perq_layer && tq == 0) { wait_bar(&bars->wq_full, wq_uses & 1); ++wq_uses; }
-                        const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l_mid]);
-                        const uint32_t a_t = tmem + kColA + (uint32_t)(l_mid & 1) * 32u;
-                        const uint32_t b_s = s_mid + mid_off[l_mid];
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(tmem + kColDmid, a_t + ks * 8, make_smem_desc(b_s + ks * 256, 128, 1024), idesc, ks > 0);
-                        mma_commit(&bars->dmid_ready);
-                        // the per-query layer's MMA of the query's last tile is complete once the NEXT layer's
-                        // input is ready: prefetch the next query's weights then
-                        if (p.perq_layer >= 0 && l_mid == p.perq_layer + 1 && tq == p.tiles_per_query - 1) {
-                            const int qn = it_mid / p.tiles_per_query + 1;
-                            if (qn < nq) {
-                                mbar_arrive_expect_tx(&bars->wq_full, 8192);
-                                bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
-                                         p.perq_img + ((size_t)stream + (size_t)qn * nstreams) * 8192, 8192, &bars->wq_full);
-                            }
-                        }
-                        if (++l_mid == p.num_mid) { l_mid = 0; ++it_mid; }
-                        progress = true;
+                // ---- per-query weight prefetch: once every tile of the resident query has issued its MMA
+                if (perq) {
+                    if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_try_wait(&bars->perq_done, (uint32_t)loaded_q & 1)) {
+                        mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                        bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
+                                 p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * 8192, 8192, &bars->wq_full);
+                        pq_loading = true;
+                    }
+                    if (pq_loading && mbar_try_wait(&bars->wq_full, (uint32_t)(loaded_q + 1) & 1)) {
+                        ++loaded_q; perq_count = 0; pq_loading = false;
                     }
                 }
+                // ---- mid layers of the two chains (they unblock the epilogue chains: priority)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (it_mid[c] >= ntiles) continue;
+                    const int l = l_mid[c];
+                    if (l == p.perq_layer && it_mid[c] / tpq != loaded_q) continue;
+                    if (!mbar_try_wait(&bars->a_ready[c], rnd[c] & 1)) continue;
+                    if (g_mid > 0 && !mbar_try_wait(&bars->dmid_free, (g_mid - 1) & 1)) continue;
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l]);
+                    const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
+                    const uint32_t b_s = s_mid + mid_off[l];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ts(tmem + kColDmid, a_t + ks * 8, make_smem_desc(b_s + ks * 256, 128, 1024), idesc, ks > 0);
+                    mma_commit(&bars->dmid_ready[c]);
+                    ++g_mid; ++rnd[c];
+                    if (l == p.perq_layer && ++perq_count == tpq) mma_commit(&bars->perq_done);
+                    if (++l_mid[c] == p.num_mid) { l_mid[c] = 0; it_mid[c] += 2; }
+                }
                 // ---- big layer chunk
-                if (it_l3 < ntiles) {
+                {
                     const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
                     const uint32_t stage = g & 1, use = g >> 1;
                     const uint32_t buf = (uint32_t)it_l3 & 1, buse = (uint32_t)it_l3 >> 1;
@@ -215,109 +227,131 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                             mma_ss(d, make_smem_desc(a_s + ks * 256, 128, 2048), make_smem_desc(b_s + ks * 256, 128, 2048), idesc_l3, ks > 0);
                         mma_commit(&bars->d3_full[stage]);
                         if (++c_l3 == 4) { mma_commit(&bars->act2_empty[buf]); c_l3 = 0; ++it_l3; }
-                        progress = true;
                     }
                 }
-                (void)progress;
             }
         }
-    } else if (warp < 4) {
-        // =============================================================== first layer + mid-layer epilogues
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        int it = 0;
-        for (int qi = 0; qi < nq; ++qi) {
-            const int q = stream + qi * nstreams;
-            // W0 * R (+ bias) for this query -> smem
-            asm volatile("bar.sync 1, 128;" ::: "memory");     // previous query's readers are done
-            if (tid < 64) {
-                float w0 = p.W0[tid * 3 + 0], w1 = p.W0[tid * 3 + 1], w2 = p.W0[tid * 3 + 2];
-                float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-                if (p.R) {
+    } else if (warp < 4 || warp >= 9) {
+        // =============================================================== first layer + mid-layer epilogues (two chains)
+        const int c = (warp < 4) ? 0 : 1;                 // chain c owns tiles c, c+2, ...; act2 buffer c; A columns c
+        const int grp = warp & 3;                         // TMEM lane quarter this warp may access
+        const int pt = grp * 32 + lane;                   // point (row) of the tile handled by this thread
+        const int ct = (warp < 4) ? tid : (tid - 9 * 32); // thread index inside the chain's warpgroup
+        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        float* wq = s_wq + c * 192;
+        const float* s_b0 = s_bias + 256;
+        const uint32_t a_col = tmem + lane_base + kColA + (uint32_t)c * 32u;
+        int cur_q = -1;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        auto fetch = [&](int it2, float& x, float& y, float& z) {
+            const int qi2 = it2 / tpq, tq2 = it2 - qi2 * tpq;
+            const size_t q2 = (size_t)stream + (size_t)qi2 * nstreams;
+            const int sgi = tq2 < p.seg[0].tiles ? 0 : 1;
+            const Seg& sg = p.seg[sgi];
+            int local = (tq2 - (sgi ? p.seg[0].tiles : 0)) * kTile + pt;
+            if (local >= sg.n) local = 0;                              // duplicate padding
+            const float* src = sg.ptr + (q2 * sg.n + local) * 3;
+            x = src[0]; y = src[1]; z = src[2];
+            if (sg.center) { x -= p.query[q2 * 3 + 0]; y -= p.query[q2 * 3 + 1]; z -= p.query[q2 * 3 + 2]; }
+        };
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (c < ntiles) fetch(c, x, y, z);
+        uint32_t round = 0;
+        for (int it = c; it < ntiles; it += 2) {
+            const int qi = it / tpq;
+            if (qi != cur_q) {
+                // (W0 * R)^T for this query -> this chain's smem copy
+                const size_t q = (size_t)stream + (size_t)qi * nstreams;
+                if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (ct < 64) {
+                    float w0 = p.W0[ct * 3 + 0], w1 = p.W0[ct * 3 + 1], w2 = p.W0[ct * 3 + 2];
+                    float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+                    if (p.R) {
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) r[i] = p.R[(size_t)q * 9 + i];
+                        for (int i = 0; i < 9; ++i) r[i] = p.R[q * 9 + i];
+                    }
+                    wq[0 * 64 + ct] = w0 * r[0] + w1 * r[3] + w2 * r[6];
+                    wq[1 * 64 + ct] = w0 * r[1] + w1 * r[4] + w2 * r[7];
+                    wq[2 * 64 + ct] = w0 * r[2] + w1 * r[5] + w2 * r[8];
                 }
-                s_wq[tid * 4 + 0] = w0 * r[0] + w1 * r[3] + w2 * r[6];
-                s_wq[tid * 4 + 1] = w0 * r[1] + w1 * r[4] + w2 * r[7];
-                s_wq[tid * 4 + 2] = w0 * r[2] + w1 * r[5] + w2 * r[8];
-                s_wq[tid * 4 + 3] = p.b0[tid];
+                if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                cur_q = qi;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const float qx = p.query[(size_t)q * 3 + 0], qy = p.query[(size_t)q * 3 + 1], qz = p.query[(size_t)q * 3 + 2];
-            for (int tq = 0; tq < p.tiles_per_query; ++tq, ++it) {
-                // ---- gather this thread's point
-                const int sgi = tq < p.seg[0].tiles ? 0 : 1;
-                const Seg& sg = p.seg[sgi];
-                int local = (tq - (sgi ? p.seg[0].tiles : 0)) * kTile + tid;
-                if (local >= sg.n) local = 0;                              // duplicate padding
-                const float* src = sg.ptr + ((size_t)q * sg.n + local) * 3;
-                float x = src[0], y = src[1], z = src[2];
-                if (sg.center) { x -= qx; y -= qy; z -= qz; }
-                // ---- layer 0 (fp32 FMA): 3 -> 64, ReLU, pack to fp16 pairs, store as the A operand in TMEM
-                {
-                    uint32_t v[32];
+            (void)qx; (void)qy; (void)qz;
+            // ---- layer 0 (fp32 FMA): 3 -> 64, ReLU, fp16 pairs, stored as the A operand in TMEM
+            {
+                uint32_t v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 wa = *reinterpret_cast<const float4*>(s_wq + (2 * j) * 4);
-                        const float4 wb = *reinterpret_cast<const float4*>(s_wq + (2 * j + 1) * 4);
-                        float ha = fmaf(wa.x, x, fmaf(wa.y, y, fmaf(wa.z, z, wa.w)));
-                        float hb = fmaf(wb.x, x, fmaf(wb.y, y, fmaf(wb.z, z, wb.w)));
-                        v[j] = pack_relu_bias(ha, hb, 0.f, 0.f);
-                    }
-                    tmem_st_x32(tmem + lane_base + kColA, v);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&bars->a_ready);
+                for (int j4 = 0; j4 < 16; ++j4) {
+                    const float4 wx = *reinterpret_cast<const float4*>(wq + 0 * 64 + 4 * j4);
+                    const float4 wy = *reinterpret_cast<const float4*>(wq + 1 * 64 + 4 * j4);
+                    const float4 wz = *reinterpret_cast<const float4*>(wq + 2 * 64 + 4 * j4);
+                    const float4 bb = *reinterpret_cast<const float4*>(s_b0 + 4 * j4);
+                    float h0 = fmaf(wx.x, x, fmaf(wy.x, y, fmaf(wz.x, z, bb.x)));
+                    float h1 = fmaf(wx.y, x, fmaf(wy.y, y, fmaf(wz.y, z, bb.y)));
+                    float h2 = fmaf(wx.z, x, fmaf(wy.z, y, fmaf(wz.z, z, bb.z)));
+                    float h3 = fmaf(wx.w, x, fmaf(wy.w, y, fmaf(wz.w, z, bb.w)));
+                    v[2 * j4] = pack_relu(h0, h1);
+                    v[2 * j4 + 1] = pack_relu(h2, h3);
                 }
-                // ---- mid layers
-                int boff = 0;
-                for (int l = 0; l < p.num_mid; ++l) {
-                    const uint32_t round = (uint32_t)(it * p.num_mid + l);
-                    wait_bar(&bars->dmid_ready, round & 1);
-                    tc_fence_after();
-                    const int N = p.mid_N[l];
-                    const bool last = (l == p.num_mid - 1);
-                    uint32_t buf = 0;
-                    if (last) {
-                        buf = (uint32_t)it & 1;
-                        wait_bar(&bars->act2_empty[buf], (((uint32_t)it >> 1) & 1) ^ 1);
+                tmem_st_x32(a_col, v);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->a_ready[c]);
+            }
+            // prefetch this chain's next point while the mid layers run
+            if (it + 2 < ntiles) fetch(it + 2, x, y, z);
+            // ---- mid layers
+            int boff = 0;
+            for (int l = 0; l < p.num_mid; ++l, ++round) {
+                wait_bar(&bars->dmid_ready[c], round & 1);
+                tc_fence_after();
+                const int N = p.mid_N[l];
+                const bool last = (l == p.num_mid - 1);
+                if (last) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
+                for (int n0 = 0; n0 < N; n0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem + lane_base + kColDmid + n0, r);
+                    tmem_ld_wait();
+                    if (n0 + 32 >= N) {            // accumulator fully read: hand D_mid to the other chain
+                        tc_fence_before();
+                        mbar_arrive(&bars->dmid_free);
                     }
-                    for (int n0 = 0; n0 < N; n0 += 32) {
-                        uint32_t r[32];
-                        tmem_ld_x32(tmem + lane_base + kColDmid + n0, r);
-                        tmem_ld_wait();
-                        uint32_t v[16];
+                    uint32_t v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = pack_relu_bias(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]),
-                                                  s_bias[boff + n0 + 2 * j], s_bias[boff + n0 + 2 * j + 1]);
-                        if (!last) {
-                            // next layer's A operand: K index = channel; columns hold channel pairs
-                            uint32_t w[8];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) w[j] = v[h * 8 + j];
-                                tmem_st_x8(tmem + lane_base + kColA + (uint32_t)((l + 1) & 1) * 32u + (uint32_t)(n0 / 2 + h * 8), w);
-                            }
-                        } else {
-                            // big layer's B operand [point row][channel K] K-major, LBO 128, SBO 2048
-                            uint8_t* dst = smem + kOffAct2 + buf * kAct2Bytes + (uint32_t)(tid >> 3) * 2048u + (uint32_t)(tid & 7) * 16u;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<uint4*>(dst + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + boff + n0 + 4 * j4);
+                        v[2 * j4] = pack_relu(__uint_as_float(r[4 * j4]) + bb.x, __uint_as_float(r[4 * j4 + 1]) + bb.y);
+                        v[2 * j4 + 1] = pack_relu(__uint_as_float(r[4 * j4 + 2]) + bb.z, __uint_as_float(r[4 * j4 + 3]) + bb.w);
                     }
                     if (!last) {
-                        tmem_st_wait();
-                        tc_fence_before();
-                        mbar_arrive(&bars->a_ready);
+                        // next layer's A operand (K index = channel, columns hold channel pairs); the MMA that read
+                        // this chain's A columns has completed (dmid_ready), so they can be overwritten in place
+                        uint32_t w[8];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = v[h * 8 + j];
+                            tmem_st_x8(a_col + (uint32_t)(n0 / 2 + h * 8), w);
+                        }
                     } else {
-                        fence_proxy_async_smem();
-                        tc_fence_before();
-                        mbar_arrive(&bars->act2_full[buf]);
+                        // big layer's B operand [point row][channel K] K-major, LBO 128, SBO 2048
+                        uint8_t* dst = smem + kOffAct2 + (uint32_t)c * kAct2Bytes + (uint32_t)(pt >> 3) * 2048u + (uint32_t)(pt & 7) * 16u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(dst + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
-                    boff += N;
                 }
+                if (!last) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->a_ready[c]);
+                } else {
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(&bars->act2_full[c]);
+                }
+                boff += N;
             }
         }
     } else {
@@ -329,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         for (int qi = 0; qi < nq; ++qi) {
             const int q = stream + qi * nstreams;
             float acc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            for (int tq = 0; tq < p.tiles_per_query; ++tq, ++it) {
+            for (int tq = 0; tq < tpq; ++tq, ++it) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t g = (uint32_t)(it * 4 + c);
@@ -344,14 +378,16 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                         tmem_ld_x32(d + n0, r0);
                         tmem_ld_x32(d + n0 + 32, r1);
                         tmem_ld_wait();
+                        if (n0 == 64) {             // accumulator fully read: release the stage before reducing
+                            tc_fence_before();
+                            mbar_arrive(&bars->d3_empty[stage]);
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
                     }
                     acc[c] = m;
-                    tc_fence_before();
-                    mbar_arrive(&bars->d3_empty[stage]);
                 }
             }
 #pragma unroll
