@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
 
             const uint32_t idesc_l3 = make_idesc_f16(128, 128);
             const uint32_t s_w3 = smem_u32(smem + kOffW3), s_mid = smem_u32(smem + kOffMid), s_act2 = smem_u32(smem + kOffAct2);
-            int it_mid[2] = {0, 1}, l_mid[2] = {0, 0};
-            uint32_t rnd[2] = {0, 0};           // per-chain (tile, layer) round counter
+            int it_mid0 = 0, it_mid1 = 1, l_mid0 = 0, l_mid1 = 0;
+            uint32_t rnd0 = 0, rnd1 = 0;        // per-chain (tile, layer) round counter
             uint32_t g_mid = 0;                 // mid MMAs issued so far (D_mid hand-over)
             int loaded_q = 0, perq_count = 0;   // per-query weights resident for local query `loaded_q`
             bool pq_loading = false;
@@ -192,13 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     }
                 }
                 // ---- mid layers of the two chains (they unblock the epilogue chains: priority)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (it_mid[c] >= ntiles) continue;
-                    const int l = l_mid[c];
-                    if (l == p.perq_layer && it_mid[c] / tpq != loaded_q) continue;
-                    if (!mbar_try_wait(&bars->a_ready[c], rnd[c] & 1)) continue;
-                    if (g_mid > 0 && !mbar_try_wait(&bars->dmid_free, (g_mid - 1) & 1)) continue;
+                auto try_mid = [&](const int c, int& it_m, int& l_m, uint32_t& rn) {
+                    if (it_m >= ntiles) return;
+                    const int l = l_m;
+                    if (l == p.perq_layer && it_m / tpq != loaded_q) return;
+                    if (!mbar_try_wait(&bars->a_ready[c], rn & 1)) return;
+                    if (g_mid > 0 && !mbar_try_wait(&bars->dmid_free, (g_mid - 1) & 1)) return;
                     tc_fence_after();
                     const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l]);
                     const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
@@ -207,10 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     for (int ks = 0; ks < 4; ++ks)
                         mma_ts(tmem + kColDmid, a_t + ks * 8, make_smem_desc(b_s + ks * 256, 128, 1024), idesc, ks > 0);
                     mma_commit(&bars->dmid_ready[c]);
-                    ++g_mid; ++rnd[c];
+                    ++g_mid; ++rn;
                     if (l == p.perq_layer && ++perq_count == tpq) mma_commit(&bars->perq_done);
-                    if (++l_mid[c] == p.num_mid) { l_mid[c] = 0; it_mid[c] += 2; }
-                }
+                    if (++l_m == p.num_mid) { l_m = 0; it_m += 2; }
+                };
+                if (g_mid & 1) { try_mid(1, it_mid1, l_mid1, rnd1); try_mid(0, it_mid0, l_mid0, rnd0); }
+                else { try_mid(0, it_mid0, l_mid0, rnd0); try_mid(1, it_mid1, l_mid1, rnd1); }
                 // ---- big layer chunk
                 {
                     const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
@@ -296,6 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
                 tmem_st_x32(a_col, v);
                 tmem_st_wait();
+                // never hold the shared D_mid accumulator while waiting for the big layer: the wait for this chain's
+                // act2 buffer happens BEFORE the MMA of the last mid layer is triggered
+                if (p.num_mid == 1) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
                 tc_fence_before();
                 mbar_arrive(&bars->a_ready[c]);
             }
@@ -308,7 +312,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 tc_fence_after();
                 const int N = p.mid_N[l];
                 const bool last = (l == p.num_mid - 1);
-                if (last) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
                 for (int n0 = 0; n0 < N; n0 += 32) {
                     uint32_t r[32];
                     tmem_ld_x32(tmem + lane_base + kColDmid + n0, r);
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
                 if (!last) {
                     tmem_st_wait();
+                    if (l == p.num_mid - 2) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
                     tc_fence_before();
                     mbar_arrive(&bars->a_ready[c]);
                 } else {
