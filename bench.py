@@ -239,12 +239,13 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     dev_ms, launches = timed(step_dev, args.steps, max(args.warmup, 3))
+    guard_total = eng.last_guard_count() if precision == 'tc' else 0   # warm-up + timed steps
     prof = eng.profile_get() if precision == 'tc' else None
     eng.profile_enable(False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
-    guard_frac = eng.last_guard_count() / max(Q, 1) if precision == 'tc' else 0.0
+    guard_frac = guard_total / max(Q * (args.steps + max(args.warmup, 3)), 1)
 
     q_total = torch.tensor([Q], dtype=torch.float64, device=dev)
     if world > 1:

@@ -181,13 +181,13 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             while (it_l3 < ntiles) {
                 // ---- per-query weight prefetch: once every tile of the resident query has issued its MMA
                 if (perq) {
-                    if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_try_wait(&bars->perq_done, (uint32_t)loaded_q & 1)) {
+                    if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_test_wait(&bars->perq_done, (uint32_t)loaded_q & 1)) {
                         mbar_arrive_expect_tx(&bars->wq_full, 8192);
                         bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
                                  p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * 8192, 8192, &bars->wq_full);
                         pq_loading = true;
                     }
-                    if (pq_loading && mbar_try_wait(&bars->wq_full, (uint32_t)(loaded_q + 1) & 1)) {
+                    if (pq_loading && mbar_test_wait(&bars->wq_full, (uint32_t)(loaded_q + 1) & 1)) {
                         ++loaded_q; perq_count = 0; pq_loading = false;
                     }
                 }
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     if (it_m >= ntiles) return;
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
-                    if (!mbar_try_wait(&bars->a_ready[c], rn & 1)) return;
-                    if (g_mid > 0 && !mbar_try_wait(&bars->dmid_free, (g_mid - 1) & 1)) return;
+                    if (!mbar_test_wait(&bars->a_ready[c], rn & 1)) return;
+                    if (g_mid > 0 && !mbar_test_wait(&bars->dmid_free, (g_mid - 1) & 1)) return;
                     tc_fence_after();
                     const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l]);
                     const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
                     const uint32_t stage = g & 1, use = g >> 1;
                     const uint32_t buf = (uint32_t)it_l3 & 1, buse = (uint32_t)it_l3 >> 1;
-                    bool ok = mbar_try_wait(&bars->d3_empty[stage], (use & 1) ^ 1);
-                    if (ok && c_l3 == 0) ok = mbar_try_wait(&bars->act2_full[buf], buse & 1);
+                    bool ok = mbar_test_wait(&bars->d3_empty[stage], (use & 1) ^ 1);
+                    if (ok && c_l3 == 0) ok = mbar_test_wait(&bars->act2_full[buf], buse & 1);
                     if (ok) {
                         tc_fence_after();
                         const uint32_t a_s = s_w3 + (uint32_t)c_l3 * 32768u, b_s = s_act2 + buf * kAct2Bytes;
