@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
     const uint32_t tmem = bars->tmem_base;
 
     if (warp == 8) {
-        // =============================================================== MMA / copy issuer (one thread)
-        if (lane == 0 && ntiles > 0) {
+        // =============================================================== MMA / copy issuer
+        // The whole warp runs the (warp-uniform) scheduling loop; one elected lane issues the asynchronous
+        // instructions (tcgen05.mma / commit / bulk copies).
+        if (ntiles > 0) {
             uint32_t bytes = kW3Bytes;
             uint32_t mid_off[3] = {0, 0, 0};
             {
@@ -157,21 +159,32 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 for (int l = 0; l < p.num_mid; ++l) { mid_off[l] = o; o += (uint32_t)p.mid_N[l] * 128u; }
                 for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u;
             }
-            mbar_arrive_expect_tx(&bars->w_full, bytes);
-            for (int c = 0; c < 4; ++c)
-                bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
-            for (int l = 0; l < p.num_mid; ++l)
-                if (l != p.perq_layer) bulk_g2s(smem + kOffMid + mid_off[l], p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
             const bool perq = p.perq_layer >= 0;
-            if (perq) {
-                mbar_arrive_expect_tx(&bars->wq_full, 8192);
-                bulk_g2s(smem + kOffMid + mid_off[p.perq_layer], p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
-                wait_bar(&bars->wq_full, 0);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars->w_full, bytes);
+                for (int c = 0; c < 4; ++c)
+                    bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
+                for (int l = 0; l < p.num_mid; ++l)
+                    if (l != p.perq_layer) bulk_g2s(smem + kOffMid + mid_off[l], p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
+                if (perq) {
+                    mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                    bulk_g2s(smem + kOffMid + mid_off[p.perq_layer], p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
+                }
             }
+            __syncwarp();
+            if (perq) wait_bar(&bars->wq_full, 0);
             wait_bar(&bars->w_full, 0);
 
+            // descriptors are built once; per MMA only the 14-bit start-address field (bytes >> 4) is advanced
             const uint32_t idesc_l3 = make_idesc_f16(128, 128);
-            const uint32_t s_w3 = smem_u32(smem + kOffW3), s_mid = smem_u32(smem + kOffMid), s_act2 = smem_u32(smem + kOffAct2);
+            const uint64_t dsc_w3 = make_smem_desc(smem_u32(smem + kOffW3), 128, 2048);
+            const uint64_t dsc_act2 = make_smem_desc(smem_u32(smem + kOffAct2), 128, 2048);
+            const uint64_t dsc_mid0 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[0], 128, 1024);
+            const uint64_t dsc_mid1 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[1], 128, 1024);
+            const uint64_t dsc_mid2 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[2], 128, 1024);
+            const uint32_t idesc_mid0 = make_idesc_f16(128, (uint32_t)p.mid_N[0]);
+            const uint32_t idesc_mid1 = make_idesc_f16(128, (uint32_t)(p.num_mid > 1 ? p.mid_N[1] : 64));
+            const uint32_t idesc_mid2 = make_idesc_f16(128, (uint32_t)(p.num_mid > 2 ? p.mid_N[2] : 64));
             int it_mid0 = 0, it_mid1 = 1, l_mid0 = 0, l_mid1 = 0;
             uint32_t rnd0 = 0, rnd1 = 0;        // per-chain (tile, layer) round counter
             uint32_t g_mid = 0;                 // mid MMAs issued so far (D_mid hand-over)
@@ -181,13 +194,16 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             while (it_l3 < ntiles) {
                 // ---- per-query weight prefetch: once every tile of the resident query has issued its MMA
                 if (perq) {
-                    if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_test_wait(&bars->perq_done, (uint32_t)loaded_q & 1)) {
-                        mbar_arrive_expect_tx(&bars->wq_full, 8192);
-                        bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
-                                 p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * 8192, 8192, &bars->wq_full);
+                    if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_test_wait_warp(&bars->perq_done, (uint32_t)loaded_q & 1)) {
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                            bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
+                                     p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * 8192, 8192, &bars->wq_full);
+                        }
+                        __syncwarp();
                         pq_loading = true;
                     }
-                    if (pq_loading && mbar_test_wait(&bars->wq_full, (uint32_t)(loaded_q + 1) & 1)) {
+                    if (pq_loading && mbar_test_wait_warp(&bars->wq_full, (uint32_t)(loaded_q + 1) & 1)) {
                         ++loaded_q; perq_count = 0; pq_loading = false;
                     }
                 }
@@ -196,18 +212,23 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     if (it_m >= ntiles) return;
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
-                    if (!mbar_test_wait(&bars->a_ready[c], rn & 1)) return;
-                    if (g_mid > 0 && !mbar_test_wait(&bars->dmid_free, (g_mid - 1) & 1)) return;
+                    if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
+                    if (g_mid > 0 && !mbar_test_wait_warp(&bars->dmid_free, (g_mid - 1) & 1)) return;
                     tc_fence_after();
-                    const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.mid_N[l]);
+                    const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
+                    const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
                     const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
-                    const uint32_t b_s = s_mid + mid_off[l];
+                    const bool pq_last = (l == p.perq_layer) && (perq_count + 1 == tpq);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ts(tmem + kColDmid, a_t + ks * 8, make_smem_desc(b_s + ks * 256, 128, 1024), idesc, ks > 0);
-                    mma_commit(&bars->dmid_ready[c]);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(tmem + kColDmid, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);
+                        mma_commit(&bars->dmid_ready[c]);
+                        if (pq_last) mma_commit(&bars->perq_done);
+                    }
+                    __syncwarp();
                     ++g_mid; ++rn;
-                    if (l == p.perq_layer && ++perq_count == tpq) mma_commit(&bars->perq_done);
+                    if (l == p.perq_layer) ++perq_count;
                     if (++l_m == p.num_mid) { l_m = 0; it_m += 2; }
                 };
                 if (g_mid & 1) { try_mid(1, it_mid1, l_mid1, rnd1); try_mid(0, it_mid0, l_mid0, rnd0); }
@@ -217,17 +238,22 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
                     const uint32_t stage = g & 1, use = g >> 1;
                     const uint32_t buf = (uint32_t)it_l3 & 1, buse = (uint32_t)it_l3 >> 1;
-                    bool ok = mbar_test_wait(&bars->d3_empty[stage], (use & 1) ^ 1);
-                    if (ok && c_l3 == 0) ok = mbar_test_wait(&bars->act2_full[buf], buse & 1);
+                    bool ok = mbar_test_wait_warp(&bars->d3_empty[stage], (use & 1) ^ 1);
+                    if (ok && c_l3 == 0) ok = mbar_test_wait_warp(&bars->act2_full[buf], buse & 1);
                     if (ok) {
                         tc_fence_after();
-                        const uint32_t a_s = s_w3 + (uint32_t)c_l3 * 32768u, b_s = s_act2 + buf * kAct2Bytes;
+                        const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c_l3 * (32768u >> 4));
+                        const uint64_t db = dsc_act2 + (uint64_t)(buf * (kAct2Bytes >> 4));
                         const uint32_t d = tmem + kColD3 + stage * 128u;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(d, make_smem_desc(a_s + ks * 256, 128, 2048), make_smem_desc(b_s + ks * 256, 128, 2048), idesc_l3, ks > 0);
-                        mma_commit(&bars->d3_full[stage]);
-                        if (++c_l3 == 4) { mma_commit(&bars->act2_empty[buf]); c_l3 = 0; ++it_l3; }
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);
+                            mma_commit(&bars->d3_full[stage]);
+                            if (c_l3 == 3) mma_commit(&bars->act2_empty[buf]);
+                        }
+                        __syncwarp();
+                        if (++c_l3 == 4) { c_l3 = 0; ++it_l3; }
                     }
                 }
             }

@@ -44,6 +44,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// warp-uniform probe: every lane tests, the vote makes the result provably uniform for the compiler (keeps the
+// issuing warp's state in uniform registers -> tcgen05.mma operands need no per-lane R2UR waterfall)
+__device__ __forceinline__ bool mbar_test_wait_warp(uint64_t* bar, uint32_t parity) {
+    return __all_sync(0xffffffffu, mbar_test_wait(bar, parity));
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (tcgen05.mma / bulk copies read smem through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
