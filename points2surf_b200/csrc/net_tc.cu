@@ -16,9 +16,9 @@
 // a per-thread reduction over TMEM columns (no shuffles).  Each CTA owns 512 of the 1024 channels (its half
 // of W3, 128 KB fp16, stays resident in shared memory); CTA 2j and 2j+1 stream the same queries.
 //
-// Warp roles (416 threads): warps 0-3 and 9-12 are two chains (even / odd tiles) doing the first layer and the
+// Warp roles (448 threads): warps 0-3 and 9-12 are two chains (even / odd tiles) doing the first layer and the
 // mid-layer epilogues (thread = point = TMEM lane), warps 4-7 the column-max epilogue of the big layer, warp 8
-// lane 0 issues every tcgen05.mma and bulk copy.
+// issues the big-layer MMAs (blocking waits), warp 13 the mid-layer MMAs of both chains (polling).
 //
 // The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
 #include "model.cuh"
@@ -35,7 +35,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kThreads = 416;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 MMA issuer | 9-12 chain 1
+constexpr int kThreads = 448;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer
 // shared memory map (bytes)
 constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
 constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
@@ -148,37 +148,64 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
     const uint32_t tmem = bars->tmem_base;
 
     if (warp == 8) {
-        // =============================================================== MMA / copy issuer
-        // The whole warp runs the (warp-uniform) scheduling loop; one elected lane issues the asynchronous
-        // instructions (tcgen05.mma / commit / bulk copies).
+        // =============================================================== big-layer MMA issuer (+ resident weight loads)
+        // The whole warp runs the warp-uniform loop; one elected lane issues the asynchronous instructions.
         if (ntiles > 0) {
-            uint32_t bytes = kW3Bytes;
+            if (lane == 0) {
+                uint32_t bytes = kW3Bytes;
+                for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u;
+                mbar_arrive_expect_tx(&bars->w_full, bytes);
+                for (int c = 0; c < 4; ++c)
+                    bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
+                uint32_t o = 0;
+                for (int l = 0; l < p.num_mid; ++l) {
+                    if (l != p.perq_layer) bulk_g2s(smem + kOffMid + o, p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
+                    else {
+                        mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                        bulk_g2s(smem + kOffMid + o, p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
+                    }
+                    o += (uint32_t)p.mid_N[l] * 128u;
+                }
+            }
+            __syncwarp();
+            wait_bar(&bars->w_full, 0);
+            const uint32_t idesc_l3 = make_idesc_f16(128, 128);
+            const uint64_t dsc_w3 = make_smem_desc(smem_u32(smem + kOffW3), 128, 2048);
+            const uint64_t dsc_act2 = make_smem_desc(smem_u32(smem + kOffAct2), 128, 2048);
+            for (int it = 0; it < ntiles; ++it) {
+                const uint32_t buf = (uint32_t)it & 1;
+                wait_bar(&bars->act2_full[buf], ((uint32_t)it >> 1) & 1);
+                const uint64_t db = dsc_act2 + (uint64_t)(buf * (kAct2Bytes >> 4));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t g = (uint32_t)(it * 4 + c);
+                    const uint32_t stage = g & 1, use = g >> 1;
+                    wait_bar(&bars->d3_empty[stage], (use & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c * (32768u >> 4));
+                        const uint32_t d = tmem + kColD3 + stage * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);
+                        mma_commit(&bars->d3_full[stage]);
+                        if (c == 3) mma_commit(&bars->act2_empty[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // =============================================================== mid-layer MMA issuer (serves the two chains)
+        if (ntiles > 0) {
             uint32_t mid_off[3] = {0, 0, 0};
             {
                 uint32_t o = 0;
                 for (int l = 0; l < p.num_mid; ++l) { mid_off[l] = o; o += (uint32_t)p.mid_N[l] * 128u; }
-                for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u;
             }
             const bool perq = p.perq_layer >= 0;
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&bars->w_full, bytes);
-                for (int c = 0; c < 4; ++c)
-                    bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
-                for (int l = 0; l < p.num_mid; ++l)
-                    if (l != p.perq_layer) bulk_g2s(smem + kOffMid + mid_off[l], p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
-                if (perq) {
-                    mbar_arrive_expect_tx(&bars->wq_full, 8192);
-                    bulk_g2s(smem + kOffMid + mid_off[p.perq_layer], p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
-                }
-            }
-            __syncwarp();
-            if (perq) wait_bar(&bars->wq_full, 0);
             wait_bar(&bars->w_full, 0);
-
-            // descriptors are built once; per MMA only the 14-bit start-address field (bytes >> 4) is advanced
-            const uint32_t idesc_l3 = make_idesc_f16(128, 128);
-            const uint64_t dsc_w3 = make_smem_desc(smem_u32(smem + kOffW3), 128, 2048);
-            const uint64_t dsc_act2 = make_smem_desc(smem_u32(smem + kOffAct2), 128, 2048);
+            if (perq) wait_bar(&bars->wq_full, 0);
             const uint64_t dsc_mid0 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[0], 128, 1024);
             const uint64_t dsc_mid1 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[1], 128, 1024);
             const uint64_t dsc_mid2 = make_smem_desc(smem_u32(smem + kOffMid) + mid_off[2], 128, 1024);
@@ -190,8 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             uint32_t g_mid = 0;                 // mid MMAs issued so far (D_mid hand-over)
             int loaded_q = 0, perq_count = 0;   // per-query weights resident for local query `loaded_q`
             bool pq_loading = false;
-            int it_l3 = 0, c_l3 = 0;
-            while (it_l3 < ntiles) {
+            while (it_mid0 < ntiles || it_mid1 < ntiles) {
                 // ---- per-query weight prefetch: once every tile of the resident query has issued its MMA
                 if (perq) {
                     if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_test_wait_warp(&bars->perq_done, (uint32_t)loaded_q & 1)) {
@@ -207,13 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                         ++loaded_q; perq_count = 0; pq_loading = false;
                     }
                 }
-                // ---- mid layers of the two chains (they unblock the epilogue chains: priority)
                 auto try_mid = [&](const int c, int& it_m, int& l_m, uint32_t& rn) {
                     if (it_m >= ntiles) return;
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
                     if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
-                    if (g_mid > 0 && !mbar_test_wait_warp(&bars->dmid_free, (g_mid - 1) & 1)) return;
+                    if (g_mid > 0) wait_bar(&bars->dmid_free, (g_mid - 1) & 1);   // short: the previous accumulator read-out
                     tc_fence_after();
                     const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
                     const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
@@ -233,32 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 };
                 if (g_mid & 1) { try_mid(1, it_mid1, l_mid1, rnd1); try_mid(0, it_mid0, l_mid0, rnd0); }
                 else { try_mid(0, it_mid0, l_mid0, rnd0); try_mid(1, it_mid1, l_mid1, rnd1); }
-                // ---- big layer chunk
-                {
-                    const uint32_t g = (uint32_t)(it_l3 * 4 + c_l3);
-                    const uint32_t stage = g & 1, use = g >> 1;
-                    const uint32_t buf = (uint32_t)it_l3 & 1, buse = (uint32_t)it_l3 >> 1;
-                    bool ok = mbar_test_wait_warp(&bars->d3_empty[stage], (use & 1) ^ 1);
-                    if (ok && c_l3 == 0) ok = mbar_test_wait_warp(&bars->act2_full[buf], buse & 1);
-                    if (ok) {
-                        tc_fence_after();
-                        const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c_l3 * (32768u >> 4));
-                        const uint64_t db = dsc_act2 + (uint64_t)(buf * (kAct2Bytes >> 4));
-                        const uint32_t d = tmem + kColD3 + stage * 128u;
-                        if (elect_one()) {
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);
-                            mma_commit(&bars->d3_full[stage]);
-                            if (c_l3 == 3) mma_commit(&bars->act2_empty[buf]);
-                        }
-                        __syncwarp();
-                        if (++c_l3 == 4) { c_l3 = 0; ++it_l3; }
-                    }
-                }
             }
         }
-    } else if (warp < 4 || warp >= 9) {
+    } else if (warp < 4 || (warp >= 9 && warp < 13)) {
         // =============================================================== first layer + mid-layer epilogues (two chains)
         const int c = (warp < 4) ? 0 : 1;                 // chain c owns tiles c, c+2, ...; act2 buffer c; A columns c
         const int grp = warp & 3;                         // TMEM lane quarter this warp may access

@@ -516,9 +516,94 @@ static void run_rate3(const char* name, int grid, int reps) {
     cudaFree(dC); cudaFree(dS);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// probe 4: TMEM -> register read bandwidth (tcgen05.ld 32x32b.x32), optionally with a concurrent MMA stream
+template <int NWARPS, bool WITH_MMA, int BATCH>
+__global__ void __launch_bounds__(NWARPS * 32 + 32) tmem_bw_probe(int reps, long long* cycles_out, float* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (32768 + 32768) / 4; e += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u ^ ((e * 2654435761u) & 0x03ff03ffu);
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (warp < NWARPS) {
+        const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ((warp >> 2) * 128);
+        float acc = 0.f;
+        __syncwarp();
+        long long t0 = clock64();
+        for (int rep = 0; rep < reps; ++rep) {
+            uint32_t r[BATCH][32];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) tmem_ld_x32(base + ((rep * BATCH + b) & 3) * 32, r[b]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) acc = fmax3(acc, __uint_as_float(r[b][0]), __uint_as_float(r[b][31]));
+        }
+        long long t1 = clock64();
+        if ((tid & 31) == 0) cycles_out[blockIdx.x * 8 + warp] = t1 - t0;
+        sink[blockIdx.x * 256 + tid] = acc;
+        if (WITH_MMA) { __syncwarp(); if (tid == 0) stop = 1; }
+    } else if (WITH_MMA && (tid & 31) == 0) {
+        // background MMA stream into columns 256..511 (N = 128, two accumulators), until the readers finish
+        const uint32_t idesc = make_idesc_f16(128, 128);
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) { da[ks] = make_smem_desc(smem_u32(smem) + ks * 256, 128, 2048); db[ks] = make_smem_desc(smem_u32(smem + 32768) + ks * 256, 128, 2048); }
+        int it = 0;
+        while (!stop && it < 200000) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) mma_ss(tmem + 256 + (it & 1) * 128, da[ks], db[ks], idesc, 1);
+            ++it;
+            if ((it & 15) == 0) { mma_commit(&bar); wait_or_trap(&bar, ((it >> 4) - 1) & 1); }   // bound the queue depth
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int NWARPS, bool WITH_MMA, int BATCH>
+static void run_tmem_bw(const char* name, int grid, int reps) {
+    long long* dC; float* dS;
+    CK(cudaMalloc(&dC, grid * 8 * 8)); CK(cudaMalloc(&dS, grid * 256 * 4));
+    CK(cudaMemset(dC, 0, grid * 64));
+    auto k = tmem_bw_probe<NWARPS, WITH_MMA, BATCH>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    k<<<grid, NWARPS * 32 + 32, 65536>>>(reps, dC, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s : KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(2); }
+    std::vector<long long> hC(grid * 8);
+    CK(cudaMemcpy(hC.data(), dC, grid * 64, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < grid * 8; ++i) if (hC[i] > mx) mx = hC[i];
+    double bytes = (double)reps * BATCH * 4096.0 * NWARPS;
+    printf("%-44s : %.1f cycles per LDTM.x32 per warp, %.1f B/cycle/SM\n", name, (double)mx / (reps * BATCH), bytes / (double)mx);
+    cudaFree(dC); cudaFree(dS);
+}
+
 int main(int argc, char** argv) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     printf("device %s sm_%d%d SMs %d\n", p.name, p.major, p.minor, p.multiProcessorCount);
+    if (argc > 1 && atoi(argv[1]) == 4) {
+        const int g = p.multiProcessorCount;
+        run_tmem_bw<4, false, 1>("tmem read 4 warps batch 1", g, 4096);
+        run_tmem_bw<4, false, 2>("tmem read 4 warps batch 2", g, 2048);
+        run_tmem_bw<4, false, 4>("tmem read 4 warps batch 4", g, 1024);
+        run_tmem_bw<8, false, 2>("tmem read 8 warps batch 2", g, 2048);
+        run_tmem_bw<8, false, 4>("tmem read 8 warps batch 4", g, 1024);
+        run_tmem_bw<1, false, 4>("tmem read 1 warp  batch 4", g, 1024);
+        run_tmem_bw<4, true, 4>("tmem read 4 warps batch 4 + MMA stream", g, 1024);
+        run_tmem_bw<8, true, 4>("tmem read 8 warps batch 4 + MMA stream", g, 1024);
+        return 0;
+    }
     if (argc > 1 && atoi(argv[1]) == 3) {
         const int g = p.multiProcessorCount;
         run_rate3<256, false, false>("r3 SS N=256", g, 512);
