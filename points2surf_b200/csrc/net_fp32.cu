@@ -101,10 +101,147 @@ gemm_nt_kernel(const float* __restrict__ A, int64_t a_stride_z, int lda,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Larger-tile variant for the shapes that carry the FLOPs (K % 16 == 0, 16-byte aligned rows):
+// 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) outputs per thread, double-buffered shared memory,
+// global loads of the next tile overlapped with the FMAs of the current one.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool COLMAX>
+__global__ void __launch_bounds__(256)
+gemm128_nt_kernel(const float* __restrict__ A, int64_t a_stride_z, int lda,
+                  const float* __restrict__ W, int64_t w_stride_z, const float* __restrict__ bias,
+                  float* __restrict__ C, int64_t c_stride_z, int ldc, int M, int N, int K, int relu) {
+    constexpr int BM = 128, BK = 16, NJ = BN / 64;          // NJ column groups of 4 per thread (64 apart)
+    constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Bs[2][BK][LDB_S];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int z = blockIdx.z;
+    const float* Az = A + (int64_t)z * a_stride_z;
+    const float* Wz = W + (int64_t)z * w_stride_z;
+    // global -> register staging: A tile 128 x 16 = 512 float4 (2 per thread), B tile BN x 16 = BN*4 float4
+    const int lr = tid >> 2, lk = (tid & 3) * 4;             // row 0..63, k offset
+    float4 ra[2], rb[BN / 64];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = m0 + lr + i * 64;
+            ra[i] = (r < M) ? *reinterpret_cast<const float4*>(Az + (int64_t)r * lda + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) {
+            const int r = n0 + lr + i * 64;
+            rb[i] = (r < N) ? *reinterpret_cast<const float4*>(Wz + (int64_t)r * K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_tile = [&](int b) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = lr + i * 64;
+            As[b][lk + 0][r] = ra[i].x; As[b][lk + 1][r] = ra[i].y; As[b][lk + 2][r] = ra[i].z; As[b][lk + 3][r] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) {
+            const int r = lr + i * 64;
+            Bs[b][lk + 0][r] = rb[i].x; Bs[b][lk + 1][r] = rb[i].y; Bs[b][lk + 2][r] = rb[i].z; Bs[b][lk + 3][r] = rb[i].w;
+        }
+    };
+    float acc[8][NJ * 4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ * 4; ++j) acc[i][j] = 0.f;
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    const int nk = K / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int b = kt & 1;
+        if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[8], w[NJ * 4];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[b][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[b][k][64 + ty * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&Bs[b][k][j * 64 + tx * 4]);
+                w[j * 4 + 0] = w4.x; w[j * 4 + 1] = w4.y; w[j * 4 + 2] = w4.z; w[j * 4 + 3] = w4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ * 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) store_tile(b ^ 1);
+        __syncthreads();
+    }
+
+    if (!COLMAX) {
+        float* Cz = C + (int64_t)z * c_stride_z;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int n = n0 + j * 64 + tx * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[e] = acc[i][j * 4 + e] + ((bias && n + e < N) ? bias[n + e] : 0.f);
+                    if (relu) v[e] = fmaxf(v[e], 0.f);
+                }
+                if (n + 3 < N && (ldc & 3) == 0) *reinterpret_cast<float4*>(Cz + (int64_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+                else
+                    for (int e = 0; e < 4; ++e)
+                        if (n + e < N) Cz[(int64_t)m * ldc + n + e] = v[e];
+            }
+        }
+    } else {
+        float* red = &As[0][0][0];          // [16][BN] floats <= 2*16*132
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NJ * 4; ++j) {
+            float v = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (m0 + (i >> 2) * 64 + ty * 4 + (i & 3) < M) v = fmaxf(v, acc[i][j]);
+            red[ty * BN + (j >> 2) * 64 + tx * 4 + (j & 3)] = v;
+        }
+        __syncthreads();
+        if (tid < BN) {
+            float v = red[tid];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) v = fmaxf(v, red[r * BN + tid]);
+            if (n0 + tid < N) atomic_max_float(C + (int64_t)z * c_stride_z + n0 + tid, v);
+        }
+    }
+}
+
+static bool gemm128_ok(const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z, int N, int K) {
+    return (K % 16 == 0) && (lda % 4 == 0) && (a_stride_z % 4 == 0) && (w_stride_z % 4 == 0) &&
+           ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && (N >= 64);
+}
+
 void launch_gemm_nt(const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z,
                     const float* bias, float* C, int64_t c_stride_z, int ldc, int M, int N, int K,
                     int batch, bool relu, cudaStream_t st) {
     if (M <= 0 || batch <= 0) return;
+    if (gemm128_ok(A, a_stride_z, lda, W, w_stride_z, N, K) && M >= 64) {
+        if (N >= 128) {
+            dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 128), (unsigned)batch);
+            P2S_LAUNCH((gemm128_nt_kernel<128, false>), g, 256, 0, st, A, a_stride_z, lda, W, w_stride_z, bias, C, c_stride_z, ldc, M, N, K, relu ? 1 : 0);
+        } else {
+            dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 64), (unsigned)batch);
+            P2S_LAUNCH((gemm128_nt_kernel<64, false>), g, 256, 0, st, A, a_stride_z, lda, W, w_stride_z, bias, C, c_stride_z, ldc, M, N, K, relu ? 1 : 0);
+        }
+        return;
+    }
     dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64), (unsigned)batch);
     const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (a_stride_z % 4 == 0) && (w_stride_z % 4 == 0) &&
                      ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0);
@@ -116,6 +253,11 @@ void launch_gemm_nt(const float* A, int64_t a_stride_z, int lda, const float* W,
 void launch_gemm_nt_colmax(const float* A, int64_t a_stride_z, int lda, const float* W, float* out,
                            int M, int N, int K, int batch, cudaStream_t st) {
     if (M <= 0 || batch <= 0) return;
+    if (gemm128_ok(A, a_stride_z, lda, W, 0, N, K) && N >= 128) {
+        dim3 g((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 128), (unsigned)batch);
+        P2S_LAUNCH((gemm128_nt_kernel<128, true>), g, 256, 0, st, A, a_stride_z, lda, W, (int64_t)0, nullptr, out, (int64_t)N, N, M, N, K, 0);
+        return;
+    }
     dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64), (unsigned)batch);
     const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (a_stride_z % 4 == 0) &&
                      ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0);
