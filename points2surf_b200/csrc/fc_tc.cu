@@ -1,0 +1,184 @@
+// Tensor-core GEMM for the per-query FC tails of the TC path (QSTN/STN heads 1024->512->256->{4,4096} and the
+// decoder 1024->512 (x2), 1024->256, 256->128; source/points_to_surf_model.py:62-64,120-122,335,343,348-350):
+//     C[M][N] = act( A[M][K] * W[N][K]^T + b ),  A fp32 row-major (converted to fp16 on the fly), W pre-packed
+//     fp16 operand images, fp32 accumulation in TMEM, C fp32 row-major.
+// One CTA per 128 x 128 output tile; K streamed in 64-wide stages (3-deep ring):
+//   warps 0-3  producers: thread = output row; load 64 fp32 of that row, convert, store as the K-major A operand;
+//              afterwards the same warps run the epilogue (TMEM -> +bias, ReLU -> global)
+//   warp 4     bulk-copies the W stage images (16 KB each) and issues the tcgen05.mma (whole warp, elect-one issue)
+// Two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's prologue/epilogue overlaps the other's MMAs.
+#include "model.cuh"
+#include "tc_ptx.cuh"
+
+namespace p2s {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr uint32_t kStageA = 128 * 64 * 2;   // 16 KB
+constexpr uint32_t kStageB = 128 * 64 * 2;   // 16 KB
+constexpr uint32_t kFcSmem = kStages * (kStageA + kStageB) + 256;
+
+struct FcBars {
+    uint64_t full[kStages], empty[kStages], d_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A, int lda, const uint8_t* __restrict__ Wimg,
+                                                    const float* __restrict__ bias, float* __restrict__ C, int ldc,
+                                                    int M, int N, int K, int relu) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * 128, nt = blockIdx.y;
+    const int nk = K / 64;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 129); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->d_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) { tmem_alloc(&bars->tmem_base, 128); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp < 4) {
+        // ---- producers: A[m0 + tid][k0 .. k0+63] -> fp16 K-major (LBO 128, SBO 1024)
+        const int row = m0 + tid;
+        const float* src = A + (int64_t)(row < M ? row : 0) * lda;
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % kStages;
+            const uint32_t use = (uint32_t)(kt / kStages);
+            // issue the global loads before waiting for the slot
+            float4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (row < M) ? *reinterpret_cast<const float4*>(src + kt * 64 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mbar_wait_bounded(&bars->empty[s], (use & 1) ^ 1);
+            uint8_t* dst = smem + s * kStageA + (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 16u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 o;
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v[2 * c].y), "f"(v[2 * c].x));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v[2 * c].w), "f"(v[2 * c].z));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(v[2 * c + 1].y), "f"(v[2 * c + 1].x));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(v[2 * c + 1].w), "f"(v[2 * c + 1].z));
+                *reinterpret_cast<uint4*>(dst + c * 128) = o;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars->full[s]);
+        }
+        // ---- epilogue
+        mbar_wait_bounded(&bars->d_full, 0);
+        tc_fence_after();
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float* dstrow = C + (int64_t)row * ldc + nt * 128;
+        const float* b = bias + nt * 128;
+#pragma unroll
+        for (int n0 = 0; n0 < 128; n0 += 32) {
+            uint32_t r[32];
+            tmem_ld_x32(tmem + lane_base + n0, r);
+            tmem_ld_wait();
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(r[j + 0]) + b[n0 + j + 0];
+                    o.y = __uint_as_float(r[j + 1]) + b[n0 + j + 1];
+                    o.z = __uint_as_float(r[j + 2]) + b[n0 + j + 2];
+                    o.w = __uint_as_float(r[j + 3]) + b[n0 + j + 3];
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(dstrow + n0 + j) = o;
+                }
+            }
+        }
+    } else {
+        // ---- W stage copies + MMA issue (warp-uniform loop, one elected lane issues)
+        const uint32_t idesc = make_idesc_f16(128, 128);
+        const uint64_t dsc_a = make_smem_desc(smem_u32(smem), 128, 1024);
+        const uint64_t dsc_b = make_smem_desc(smem_u32(smem + kStages * kStageA), 128, 1024);
+        const uint8_t* wsrc = Wimg + (size_t)nt * nk * kStageB;
+        // prefetch the first stages of W
+        for (int kt = 0; kt < nk && kt < kStages; ++kt) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&bars->full[kt], kStageB);
+                bulk_g2s(smem + kStages * kStageA + kt * kStageB, wsrc + (size_t)kt * kStageB, kStageB, &bars->full[kt]);
+            }
+            __syncwarp();
+        }
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % kStages;
+            const uint32_t use = (uint32_t)(kt / kStages);
+            mbar_wait_bounded(&bars->full[s], use & 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem, dsc_a + (uint64_t)(s * (kStageA >> 4) + ks * 16), dsc_b + (uint64_t)(s * (kStageB >> 4) + ks * 16), idesc, (kt | ks) > 0);
+                mma_commit(&bars->empty[s]);
+                if (kt == nk - 1) mma_commit(&bars->d_full);
+            }
+            __syncwarp();
+            // refill the slot used one step earlier (its MMAs have had a full stage of time to drain) with the W
+            // image of k-step (kt - 1) + kStages
+            if (kt >= 1) {
+                const int kp = kt - 1, kn = kp + kStages;
+                if (kn < nk) {
+                    const int sp = kp % kStages;
+                    mbar_wait_bounded(&bars->empty[sp], (uint32_t)(kp / kStages) & 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bars->full[sp], kStageB);
+                        bulk_g2s(smem + kStages * kStageA + sp * kStageB, wsrc + (size_t)kn * kStageB, kStageB, &bars->full[sp]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// fp32 W[N][K] -> images [N/128][K/64][128 x 64 fp16, K-major, LBO 128, SBO 1024]
+__global__ void pack_fc_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ img) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)N * K) return;
+    int n = (int)(e / K), k = (int)(e % K);
+    int nt = n >> 7, r = n & 127, kt = k >> 6, kk = k & 63;
+    size_t off = ((size_t)nt * (K / 64) + kt) * kStageB + (size_t)(r >> 3) * 1024 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__half*>(img + off) = __float2half_rn(W[e]);
+}
+
+}  // namespace
+
+bool fc_tc_supported(int N, int K) { return (N % 128 == 0) && (K % 64 == 0) && N >= 128 && K >= 64; }
+
+uint8_t* fc_tc_pack(const Layer& L, std::vector<void*>& allocs) {
+    P2S_CHECK(fc_tc_supported(L.cout, L.cin), "layer shape not supported by the tensor-core FC kernel");
+    void* p = nullptr;
+    P2S_CUDA(cudaMalloc(&p, (size_t)L.cout * L.cin * 2));
+    allocs.push_back(p);
+    P2S_LAUNCH(pack_fc_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, (uint8_t*)p);
+    return (uint8_t*)p;
+}
+
+void fc_tc_init() {
+    static bool done = false;
+    if (!done) {
+        P2S_CUDA(cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmem));
+        done = true;
+    }
+}
+
+void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
+                  int64_t M, int N, int K, bool relu, cudaStream_t st) {
+    if (M <= 0) return;
+    P2S_CHECK(fc_tc_supported(N, K) && lda % 4 == 0 && ldc % 4 == 0, "bad FC shape for the tensor-core kernel");
+    dim3 grid((unsigned)cdiv(M, 128), (unsigned)(N / 128), 1);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0);
+}
+
+}  // namespace p2s

@@ -494,9 +494,18 @@ struct TcStack {           // one conv stack ending in the 128 -> 1024 layer
     const float* b3 = nullptr;
 };
 
+struct TcFc {                 // one Linear layer: fp32 weights + (optional) tensor-core operand images
+    const Layer* L = nullptr;
+    const uint8_t* img = nullptr;
+};
+struct TcStnFc { TcFc fc1, fc2, fc3; };
+
 struct TcWeights {
     TcStack qstn;                // pass A
     TcStack stn[2], fin[2];      // [0] local, [1] global: pass B, pass C
+    TcStnFc qstn_fc, stn_fc[2];
+    TcFc head_fc1[2], head_fc2, head_fc3;
+    bool fc_on_tc = true;
     std::vector<void*> allocs;
     int sm_count = 148;
     // profile of the dominant kernel (bench.py roofline)
@@ -569,13 +578,19 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
 
 Seg make_seg(const float* ptr, int n, int center) { return Seg{ptr, n, n > 0 ? (n + kTile - 1) / kTile : 0, center}; }
 
-void fc_tail(const Layer& b3src, const Stn& s, const float* gmax_raw, int64_t Bc, float* g, float* f1, float* f2, float* out, cudaStream_t st) {
+void run_fc(const TcFc& f, const float* in, int lda, float* out, int ldc, int64_t Bc, bool relu, bool on_tc, cudaStream_t st) {
+    const Layer& L = *f.L;
+    if (on_tc && f.img) launch_fc_tc(in, lda, f.img, L.b, out, ldc, Bc, L.cout, L.cin, relu, st);
+    else launch_gemm_nt(in, 0, lda, L.W, 0, L.b, out, 0, ldc, (int)Bc, L.cout, L.cin, 1, relu, st);
+}
+
+void fc_tail(const Layer& b3src, const TcStnFc& s, bool on_tc, const float* gmax_raw, int64_t Bc, float* g, float* f1, float* f2, float* out, cudaStream_t st) {
     // g = relu(max + b3) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
     P2S_CUDA(cudaMemcpyAsync(g, gmax_raw, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
     launch_bias_act(g, b3src.b, Bc, 1024, true, st);
-    launch_gemm_nt(g, 0, 1024, s.fc1.W, 0, s.fc1.b, f1, 0, 512, (int)Bc, 512, 1024, 1, true, st);
-    launch_gemm_nt(f1, 0, 512, s.fc2.W, 0, s.fc2.b, f2, 0, 256, (int)Bc, 256, 512, 1, true, st);
-    launch_gemm_nt(f2, 0, 256, s.fc3.W, 0, s.fc3.b, out, 0, s.fc3.cout, (int)Bc, s.fc3.cout, 256, 1, false, st);
+    run_fc(s.fc1, g, 1024, f1, 512, Bc, true, on_tc, st);
+    run_fc(s.fc2, f1, 512, f2, 256, Bc, true, on_tc, st);
+    run_fc(s.fc3, f2, 256, out, s.fc3.L->cout, Bc, false, on_tc, st);
 }
 
 }  // namespace
@@ -613,6 +628,26 @@ void tc_build(Model& m) {
         s.w3_img = pack_w3(*t, f.conv3);
         s.b3 = f.conv3.b;
     };
+    fc_tc_init();
+    {
+        const char* e = getenv("P2S_FC_FP32");
+        t->fc_on_tc = !(e && e[0] == '1');
+    }
+    auto mk_fc = [&](const Layer& L) {
+        TcFc f;
+        f.L = &L;
+        f.img = fc_tc_supported(L.cout, L.cin) ? fc_tc_pack(L, t->allocs) : nullptr;
+        return f;
+    };
+    auto mk_stn_fc = [&](const Stn& s) { TcStnFc r; r.fc1 = mk_fc(s.fc1); r.fc2 = mk_fc(s.fc2); r.fc3 = mk_fc(s.fc3); return r; };
+    if (m.shared_qstn) t->qstn_fc = mk_stn_fc(m.point_stn);
+    else if (m.global.has_qstn) t->qstn_fc = mk_stn_fc(m.global.stn1);
+    t->stn_fc[0] = mk_stn_fc(m.local.stn2);
+    t->stn_fc[1] = mk_stn_fc(m.global.stn2);
+    t->head_fc1[0] = mk_fc(m.fc1_local);
+    t->head_fc1[1] = mk_fc(m.fc1_global);
+    t->head_fc2 = mk_fc(m.fc2);
+    t->head_fc3 = mk_fc(m.fc3);
     if (m.shared_qstn) build_stn(t->qstn, m.point_stn, nullptr, nullptr);
     else if (m.global.has_qstn) build_stn(t->qstn, m.global.stn1, nullptr, nullptr);
     build_stn(t->stn[0], m.local.stn2, &m.local.conv0a, &m.local.conv0b);
@@ -673,12 +708,12 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
             launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st);
-            fc_tail(m.point_stn.c3, m.point_stn, gmax, Bc, g, f1, f2, q4, st);
+            fc_tail(m.point_stn.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
             launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st);
-            fc_tail(m.global.stn1.c3, m.global.stn1, gmax, Bc, g, f1, f2, q4, st);
+            fc_tail(m.global.stn1.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         }
@@ -688,7 +723,7 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
             launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st);
-            fc_tail(f.stn2.c3, f.stn2, gmax, Bc, g, f1, f2, T, st);
+            fc_tail(f.stn2.c3, t.stn_fc[br], t.fc_on_tc, gmax, Bc, g, f1, f2, T, st);
             launch_add_identity64(T, Bc, st);
             // W1' = conv1.W * T  -> per-query fp16 operand images
             P2S_LAUNCH(transpose64_kernel, (unsigned)cdiv(Bc * 4096, 256), 256, 0, st, T, Tt, Bc);
@@ -699,10 +734,10 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
-        launch_gemm_nt(fmax_l, 0, 1024, m.fc1_local.W, 0, m.fc1_local.b, cat, 0, 1024, (int)Bc, 512, 1024, 1, true, st);
-        launch_gemm_nt(fmax_g, 0, 1024, m.fc1_global.W, 0, m.fc1_global.b, cat + 512, 0, 1024, (int)Bc, 512, 1024, 1, true, st);
-        launch_gemm_nt(cat, 0, 1024, m.fc2.W, 0, m.fc2.b, h3, 0, 256, (int)Bc, 256, 1024, 1, true, st);
-        launch_gemm_nt(h3, 0, 256, m.fc3.W, 0, m.fc3.b, h4, 0, 128, (int)Bc, 128, 256, 1, true, st);
+        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, t.fc_on_tc, st);
+        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, t.fc_on_tc, st);
+        run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, t.fc_on_tc, st);
+        run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, t.fc_on_tc, st);
         launch_gemm_nt(h4, 0, 128, m.fc4.W, 0, m.fc4.b, logits + b0 * 2, 0, 2, (int)Bc, 2, 128, 1, false, st);
     }
 

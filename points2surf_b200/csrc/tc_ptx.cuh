@@ -30,6 +30,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// blocking wait that traps (kernel error) instead of hanging the GPU if a barrier protocol bug slips in
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) __trap();
+    }
+}
 // non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is incomplete)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
