@@ -1,11 +1,15 @@
 // Tensor-core GEMM for the per-query FC tails of the TC path (QSTN/STN heads 1024->512->256->{4,4096} and the
 // decoder 1024->512 (x2), 1024->256, 256->128; source/points_to_surf_model.py:62-64,120-122,335,343,348-350):
-//     C[M][N] = act( A[M][K] * W[N][K]^T + b ),  A fp32 row-major (converted to fp16 on the fly), W pre-packed
-//     fp16 operand images, fp32 accumulation in TMEM, C fp32 row-major.
-// One CTA per 128 x 128 output tile; K streamed in 64-wide stages (3-deep ring):
-//   warps 0-3  producers: thread = output row; load 64 fp32 of that row, convert, store as the K-major A operand;
+//     C[M][N] = act( A[M][K] * W[N][K]^T + b ),  A fp32 row-major, W pre-packed operand images, fp32 accumulation
+//     in TMEM, C fp32 row-major.
+// These layers produce the point rotation, the 64x64 feature transform and the logits, so they keep fp32-level
+// accuracy: every fp32 operand x is split into two fp16 numbers x_hi + x_lo (x_hi = fp16(x), x_lo = fp16(x - x_hi))
+// and the product is evaluated as A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (the dropped lo*lo term is ~2^-22 relative).
+// Three tensor-core passes cost nothing here: the FC tails are 1 % of the network's FLOPs.
+// One CTA per 128 x 128 output tile; K streamed in 32-wide stages (3-deep ring):
+//   warps 0-3  producers: thread = output row; load 32 fp32 of that row, split, store the two K-major A operands;
 //              afterwards the same warps run the epilogue (TMEM -> +bias, ReLU -> global)
-//   warp 4     bulk-copies the W stage images (16 KB each) and issues the tcgen05.mma (whole warp, elect-one issue)
+//   warp 4     bulk-copies the W stage images (hi + lo, 16 KB) and issues the tcgen05.mma (elect-one issue)
 // Two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's prologue/epilogue overlaps the other's MMAs.
 #include "model.cuh"
 #include "tc_ptx.cuh"
@@ -17,8 +21,10 @@ using namespace ptx;
 namespace {
 
 constexpr int kStages = 3;
-constexpr uint32_t kStageA = 128 * 64 * 2;   // 16 KB
-constexpr uint32_t kStageB = 128 * 64 * 2;   // 16 KB
+constexpr int kBK = 32;
+constexpr uint32_t kHalf = 128 * kBK * 2;     // one 128 x 32 fp16 operand image: 8 KB (K-major, LBO 128, SBO 512)
+constexpr uint32_t kStageA = 2 * kHalf;       // hi + lo
+constexpr uint32_t kStageB = 2 * kHalf;       // hi + lo
 constexpr uint32_t kFcSmem = kStages * (kStageA + kStageB) + 256;
 
 struct FcBars {
@@ -33,7 +39,7 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
     FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.x * 128, nt = blockIdx.y;
-    const int nk = K / 64;
+    const int nk = K / kBK;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 129); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->d_full, 1);
@@ -46,26 +52,32 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
     const uint32_t tmem = bars->tmem_base;
 
     if (warp < 4) {
-        // ---- producers: A[m0 + tid][k0 .. k0+63] -> fp16 K-major (LBO 128, SBO 1024)
+        // ---- producers: A[m0 + tid][k0 .. k0+31] -> fp16 hi / lo, K-major (LBO 128, SBO 512)
         const int row = m0 + tid;
         const float* src = A + (int64_t)(row < M ? row : 0) * lda;
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % kStages;
             const uint32_t use = (uint32_t)(kt / kStages);
             // issue the global loads before waiting for the slot
-            float4 v[16];
+            float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (row < M) ? *reinterpret_cast<const float4*>(src + kt * 64 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) v[j] = (row < M) ? *reinterpret_cast<const float4*>(src + kt * kBK + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait_bounded(&bars->empty[s], (use & 1) ^ 1);
-            uint8_t* dst = smem + s * kStageA + (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 16u;
+            uint8_t* dst = smem + s * kStageA + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 16u;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 o;
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v[2 * c].y), "f"(v[2 * c].x));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v[2 * c].w), "f"(v[2 * c].z));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(v[2 * c + 1].y), "f"(v[2 * c + 1].x));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(v[2 * c + 1].w), "f"(v[2 * c + 1].z));
-                *reinterpret_cast<uint4*>(dst + c * 128) = o;
+            for (int c = 0; c < 4; ++c) {
+                const float x[8] = {v[2 * c].x, v[2 * c].y, v[2 * c].z, v[2 * c].w, v[2 * c + 1].x, v[2 * c + 1].y, v[2 * c + 1].z, v[2 * c + 1].w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                    float2 hf = __half22float2(h);
+                    __half2 l = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+                    hi[e] = *reinterpret_cast<uint32_t*>(&h);
+                    lo[e] = *reinterpret_cast<uint32_t*>(&l);
+                }
+                *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + kHalf + c * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars->full[s]);
@@ -97,8 +109,8 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
     } else {
         // ---- W stage copies + MMA issue (warp-uniform loop, one elected lane issues)
         const uint32_t idesc = make_idesc_f16(128, 128);
-        const uint64_t dsc_a = make_smem_desc(smem_u32(smem), 128, 1024);
-        const uint64_t dsc_b = make_smem_desc(smem_u32(smem + kStages * kStageA), 128, 1024);
+        const uint64_t dsc_a = make_smem_desc(smem_u32(smem), 128, 512);
+        const uint64_t dsc_b = make_smem_desc(smem_u32(smem + kStages * kStageA), 128, 512);
         const uint8_t* wsrc = Wimg + (size_t)nt * nk * kStageB;
         // prefetch the first stages of W
         for (int kt = 0; kt < nk && kt < kStages; ++kt) {
@@ -114,9 +126,14 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             mbar_wait_bounded(&bars->full[s], use & 1);
             tc_fence_after();
             if (elect_one()) {
+                const uint64_t a_hi = dsc_a + (uint64_t)(s * (kStageA >> 4)), a_lo = a_hi + (uint64_t)(kHalf >> 4);
+                const uint64_t b_hi = dsc_b + (uint64_t)(s * (kStageB >> 4)), b_lo = b_hi + (uint64_t)(kHalf >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem, dsc_a + (uint64_t)(s * (kStageA >> 4) + ks * 16), dsc_b + (uint64_t)(s * (kStageB >> 4) + ks * 16), idesc, (kt | ks) > 0);
+                for (int ks = 0; ks < kBK / 16; ++ks) {
+                    mma_ss(tmem, a_lo + (uint64_t)(ks * 16), b_hi + (uint64_t)(ks * 16), idesc, (kt | ks) > 0);   // small terms first
+                    mma_ss(tmem, a_hi + (uint64_t)(ks * 16), b_lo + (uint64_t)(ks * 16), idesc, 1);
+                    mma_ss(tmem, a_hi + (uint64_t)(ks * 16), b_hi + (uint64_t)(ks * 16), idesc, 1);
+                }
                 mma_commit(&bars->empty[s]);
                 if (kt == nk - 1) mma_commit(&bars->d_full);
             }
@@ -142,24 +159,27 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
     if (warp == 4) tmem_dealloc(tmem, 128);
 }
 
-// fp32 W[N][K] -> images [N/128][K/64][128 x 64 fp16, K-major, LBO 128, SBO 1024]
+// fp32 W[N][K] -> images [N/128][K/32][hi | lo][128 x 32 fp16, K-major, LBO 128, SBO 512]
 __global__ void pack_fc_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ img) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)N * K) return;
     int n = (int)(e / K), k = (int)(e % K);
-    int nt = n >> 7, r = n & 127, kt = k >> 6, kk = k & 63;
-    size_t off = ((size_t)nt * (K / 64) + kt) * kStageB + (size_t)(r >> 3) * 1024 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
-    *reinterpret_cast<__half*>(img + off) = __float2half_rn(W[e]);
+    int nt = n >> 7, r = n & 127, kt = k / kBK, kk = k % kBK;
+    size_t off = ((size_t)nt * (K / kBK) + kt) * kStageB + (size_t)(r >> 3) * 512 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+    const float w = W[e];
+    const __half h = __float2half_rn(w);
+    *reinterpret_cast<__half*>(img + off) = h;
+    *reinterpret_cast<__half*>(img + off + kHalf) = __float2half_rn(w - __half2float(h));
 }
 
 }  // namespace
 
-bool fc_tc_supported(int N, int K) { return (N % 128 == 0) && (K % 64 == 0) && N >= 128 && K >= 64; }
+bool fc_tc_supported(int N, int K) { return (N % 128 == 0) && (K % kBK == 0) && N >= 128 && K >= kBK; }
 
 uint8_t* fc_tc_pack(const Layer& L, std::vector<void*>& allocs) {
     P2S_CHECK(fc_tc_supported(L.cout, L.cin), "layer shape not supported by the tensor-core FC kernel");
     void* p = nullptr;
-    P2S_CUDA(cudaMalloc(&p, (size_t)L.cout * L.cin * 2));
+    P2S_CUDA(cudaMalloc(&p, (size_t)L.cout * L.cin * 4));
     allocs.push_back(p);
     P2S_LAUNCH(pack_fc_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, (uint8_t*)p);
     return (uint8_t*)p;

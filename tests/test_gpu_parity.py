@@ -354,4 +354,4 @@ def test_reconstruct_tc_close_to_fp32():
     assert torch.equal(lin_a, lin_b)
     a, b = sdf_a.cpu().numpy(), sdf_b.cpu().numpy()
     assert np.array_equal(np.sign(a), np.sign(b))
-    assert np.abs(a - b).max() < 5e-3
+    assert np.abs(a - b).max() < 1e-2   # |d| = tanh(l0)^2 r with r ~ 0.4: a logit error of 0.03 moves the SDF by < 1e-2
