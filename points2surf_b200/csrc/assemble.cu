@@ -232,9 +232,13 @@ __global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, int S,
     }
 }
 
+// CACHE: the per-point clock values live in dynamic shared memory (N floats) so that the distance, the Philox
+// block (shared by 4 consecutive points) and the logarithm are evaluated once per point instead of once per pass.
+template <bool CACHE>
 __global__ void __launch_bounds__(kThreads)
 subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries,
                           int64_t qbase, int S, uint64_t seed, int32_t* __restrict__ out, int* __restrict__ err_flag) {
+    extern __shared__ float s_key[];     // [N] when CACHE
     __shared__ SelectSmem s;
     __shared__ float red[kThreads / 32];
     __shared__ float s_dmax;
@@ -243,8 +247,11 @@ subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __r
     const float qx = queries[q * 3 + 0], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
     // dist_prob (utils.py:200-208): float32 like NumPy
     float dmax = 0.f;
-    for (int i = tid; i < N; i += kThreads)
-        dmax = fmaxf(dmax, norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2])));
+    for (int i = tid; i < N; i += kThreads) {
+        float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
+        if (CACHE) s_key[i] = d;
+        dmax = fmaxf(dmax, d);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     if ((tid & 31) == 0) red[tid >> 5] = dmax;
@@ -257,17 +264,32 @@ subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __r
     __syncthreads();
     dmax = s_dmax;
     const uint64_t qi = (uint64_t)(qbase + q);
-    auto keyfn = [&](int i) {
-        float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
+    // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
+    auto clock_of = [&](float d, uint32_t rnd) {
         float dn = __fdiv_rn(d, dmax);
         float w = __fsub_rn(1.0f, __fmul_rn(1.5f, dn));
         w = fminf(fmaxf(w, 0.05f), 1.0f);
+        return __fdividef(-__logf(u01_open(rnd)), w);
+    };
+    if (CACHE) {
+        // one Philox block per 4 consecutive points
+        for (int i4 = tid; i4 * 4 < N; i4 += kThreads) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)i4, 0x77f1e2d3u, r);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i4 * 4 + e;
+                if (i < N) s_key[i] = clock_of(s_key[i], r[e]);
+            }
+        }
+        __syncthreads();
+    }
+    auto keyfn = [&](int i) {
+        if (CACHE) return dkey((double)s_key[i]);
+        float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
         uint32_t r[4];
         philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)(i >> 2), 0x77f1e2d3u, r);
-        float u = u01_open(r[i & 3]);
-        // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
-        double e = (double)(-__logf(u)) / (double)w;
-        return dkey(e);
+        return dkey((double)clock_of(d, r[i & 3]));
     };
     find_boundary(s, N, S, kCap, keyfn);
     if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
@@ -341,7 +363,17 @@ void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int
         int64_t threads = Q * ((S + 3) / 4);
         P2S_LAUNCH(subsample_uniform_kernel, (unsigned)cdiv(threads, 256), 256, 0, st, (int)N, Q, qbase, S, seed, out);
     } else if (mode == P2S_SUBSAMPLE_WEIGHTED) {
-        P2S_LAUNCH(subsample_weighted_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+        const size_t cache_bytes = (size_t)N * sizeof(float);
+        if (cache_bytes <= 160 * 1024) {
+            static thread_local bool attr_set = false;
+            if (!attr_set) {
+                P2S_CUDA(cudaFuncSetAttribute(subsample_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_set = true;
+            }
+            P2S_LAUNCH(subsample_weighted_kernel<true>, (unsigned)Q, kThreads, cache_bytes, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+        } else {
+            P2S_LAUNCH(subsample_weighted_kernel<false>, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+        }
     } else {
         throw Error("unknown sub-sample mode");
     }

@@ -355,3 +355,15 @@ def test_reconstruct_tc_close_to_fp32():
     a, b = sdf_a.cpu().numpy(), sdf_b.cpu().numpy()
     assert np.array_equal(np.sign(a), np.sign(b))
     assert np.abs(a - b).max() < 1e-2   # |d| = tanh(l0)^2 r with r ~ 0.4: a logit error of 0.03 moves the SDF by < 1e-2
+
+
+def test_subsample_weighted_large_cloud_uncached_path():
+    # N * 4 B > 160 KB: the kernel recomputes the clocks per pass instead of caching them in shared memory
+    rng = np.random.RandomState(2)
+    cloud = rng.uniform(-0.9, 0.9, (50000, 3)).astype(np.float32)
+    q = cu(cloud[:5] + np.float32(0.01))
+    ids = ops.subsample(cu(cloud), q, 1000, False, seed=3).cpu().numpy()
+    assert ids.min() >= 0 and ids.max() < 50000
+    assert all(len(set(r.tolist())) == 1000 for r in ids)
+    d = np.linalg.norm(cloud[ids[0]] - cloud[0], axis=1)
+    assert d.mean() < np.linalg.norm(cloud - cloud[0], axis=1).mean()      # near points are favoured
