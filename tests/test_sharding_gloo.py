@@ -1,0 +1,63 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (shape / slab sharding, timing reduction, band gather)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from points2surf_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        Q = 1001
+        first, count = sharding.query_slab(Q, rank, world)
+        full = torch.arange(Q, dtype=torch.float32) * 0.5
+        slab = full[first:first + count].clone()                      # stand-in for Engine.reconstruct(first, count)
+        counts = [sharding.query_slab(Q, r, world)[1] for r in range(world)]
+        band = sharding.gather_band(slab, counts)
+        ms, units = sharding.reduce_timing(10.0 + rank, count)
+        q.put((rank, sharding.shapes_for_rank(7, rank, world), first, count, bool(torch.equal(band, full)), ms, units))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, s0, f0, c0, ok0, ms0, u0), (r1, s1, f1, c1, ok1, ms1, u1) = res
+    assert s0 == [0, 2, 4, 6] and s1 == [1, 3, 5]
+    assert (f0, c0) == (0, 501) and (f1, c1) == (501, 500)
+    assert ok0 and ok1
+    assert ms0 == ms1 == 11.0 and u0 == u1 == 1001.0
+
+
+def test_slabs_partition_every_size():
+    for Q in (0, 1, 5, 152637):
+        for world in (1, 2, 3, 8):
+            slabs = [sharding.query_slab(Q, r, world) for r in range(world)]
+            assert slabs[0][0] == 0 and sum(c for _, c in slabs) == Q
+            for (f, c), (f2, _) in zip(slabs, slabs[1:]):
+                assert f + c == f2
+            assert max(c for _, c in slabs) - min(c for _, c in slabs) <= 1
