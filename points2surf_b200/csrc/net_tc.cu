@@ -44,12 +44,13 @@ constexpr uint32_t kOffW3 = 0;
 constexpr uint32_t kOffMid = kOffW3 + kW3Bytes;
 constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
 constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;
-constexpr uint32_t kSmallBytes = 2 * 192 * 4 + 320 * 4 + 144;  // Wq[2 chains][3][64], biases[256 mid + 64 first], barriers
+constexpr uint32_t kSmallBytes = 2 * 192 * 4 + 320 * 4 + 152;  // Wq[2 chains][3][64], biases[256 mid + 64 first], barriers
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM map (columns)
 constexpr uint32_t kColD3 = 0;      // 2 stages x 128
-constexpr uint32_t kColDmid = 256;  // 128, shared by the two chains (dmid_free hand-over)
+constexpr uint32_t kColDmid = 256;  // 128 columns: accumulator of the 128-channel mid layers (shared by the chains)
+constexpr uint32_t kColDmidB = 448; // 64 columns: accumulator of the 64-channel mid layers (shared by the chains)
 constexpr uint32_t kColA = 384;     // 2 chains x 32 (fp16 pairs, K = 64)
 
 struct Seg {
@@ -78,12 +79,13 @@ struct PassParams {
 };
 
 struct Bars {
-    uint64_t w_full, wq_full, perq_done, dmid_free;
+    uint64_t w_full, wq_full, perq_done;
+    uint64_t dmid_free[2];      // [0]: 128-column accumulator, [1]: 64-column accumulator
     uint64_t a_ready[2], dmid_ready[2];
     uint64_t act2_full[2], act2_empty[2], d3_full[2], d3_empty[2];
     uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 144, "barrier block");
+static_assert(sizeof(Bars) <= 152, "barrier block");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 #if P2S_TC_BOUNDED_WAIT
@@ -122,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         mbar_init(&bars->w_full, 1);
         mbar_init(&bars->wq_full, 1);
         mbar_init(&bars->perq_done, 1);
-        mbar_init(&bars->dmid_free, 128);
+        mbar_init(&bars->dmid_free[0], 128);
+        mbar_init(&bars->dmid_free[1], 128);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->a_ready[i], 128);
             mbar_init(&bars->dmid_ready[i], 1);
@@ -214,7 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             const uint32_t idesc_mid2 = make_idesc_f16(128, (uint32_t)(p.num_mid > 2 ? p.mid_N[2] : 64));
             int it_mid0 = 0, it_mid1 = 1, l_mid0 = 0, l_mid1 = 0;
             uint32_t rnd0 = 0, rnd1 = 0;        // per-chain (tile, layer) round counter
-            uint32_t g_mid = 0;                 // mid MMAs issued so far (D_mid hand-over)
+            uint32_t g_mid = 0;                 // mid MMAs issued so far (alternates which chain is polled first)
+            uint32_t g_buf0 = 0, g_buf1 = 0;    // MMAs issued into the 128-column / 64-column accumulator
             int loaded_q = 0, perq_count = 0;   // per-query weights resident for local query `loaded_q`
             bool pq_loading = false;
             while (it_mid0 < ntiles || it_mid1 < ntiles) {
@@ -238,21 +242,24 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
                     if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
-                    if (g_mid > 0) wait_bar(&bars->dmid_free, (g_mid - 1) & 1);   // short: the previous accumulator read-out
+                    const bool small = (p.mid_N[l] == 64);
+                    uint32_t& g_buf = small ? g_buf1 : g_buf0;
+                    if (g_buf > 0) wait_bar(&bars->dmid_free[small ? 1 : 0], (g_buf - 1) & 1);   // short: the previous read-out
                     tc_fence_after();
                     const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
                     const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
                     const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
+                    const uint32_t d_t = tmem + (small ? kColDmidB : kColDmid);
                     const bool pq_last = (l == p.perq_layer) && (perq_count + 1 == tpq);
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(tmem + kColDmid, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);
+                            mma_ts(d_t, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);
                         mma_commit(&bars->dmid_ready[c]);
                         if (pq_last) mma_commit(&bars->perq_done);
                     }
                     __syncwarp();
-                    ++g_mid; ++rn;
+                    ++g_mid; ++g_buf; ++rn;
                     if (l == p.perq_layer) ++perq_count;
                     if (++l_m == p.num_mid) { l_m = 0; it_m += 2; }
                 };
@@ -340,13 +347,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 tc_fence_after();
                 const int N = p.mid_N[l];
                 const bool last = (l == p.num_mid - 1);
+                const uint32_t dcol = (N == 64) ? kColDmidB : kColDmid;
                 for (int n0 = 0; n0 < N; n0 += 32) {
                     uint32_t r[32];
-                    tmem_ld_x32(tmem + lane_base + kColDmid + n0, r);
+                    tmem_ld_x32(tmem + lane_base + dcol + n0, r);
                     tmem_ld_wait();
-                    if (n0 + 32 >= N) {            // accumulator fully read: hand D_mid to the other chain
+                    if (n0 + 32 >= N) {            // accumulator fully read: hand it to the other chain
                         tc_fence_before();
-                        mbar_arrive(&bars->dmid_free);
+                        mbar_arrive(&bars->dmid_free[N == 64 ? 1 : 0]);
                     }
                     uint32_t v[16];
 #pragma unroll
