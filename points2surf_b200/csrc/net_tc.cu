@@ -461,6 +461,39 @@ __global__ void pack_perq_kernel(const float* __restrict__ W, int64_t B, uint8_t
     *reinterpret_cast<__half*>(img + b * 8192 + off) = __float2half_rn(W[e]);
 }
 
+// Fused per-query fold: img[b] = fp16 operand image of W1 * (T[b] + I), T[b] = the STN's raw fc3 output
+// viewed as [64][64] (model.py:66-68,196,201).  One CTA per query, 256 threads, W1 and T staged in shared memory.
+__global__ void __launch_bounds__(256) fold_w1_kernel(const float* __restrict__ W1, const float* __restrict__ T, int64_t B, uint8_t* __restrict__ img) {
+    __shared__ float sW[64][65];
+    __shared__ float sT[64][65];
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 4096; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        sW[r][c] = W1[e];
+        sT[r][c] = T[b * 4096 + e] + (r == c ? 1.0f : 0.0f);
+    }
+    __syncthreads();
+    // thread -> output row o = tid / 4, 16 consecutive input columns i0 = (tid % 4) * 16
+    const int o = tid >> 2, i0 = (tid & 3) * 16;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int j = 0; j < 64; ++j) {
+        const float w = sW[o][j];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(w, sT[j][i0 + i], acc[i]);
+    }
+    uint8_t* dst = img + b * 8192 + (uint32_t)(o >> 3) * 1024u + (uint32_t)(o & 7) * 16u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = pack_half2(acc[h * 8 + 2 * e], acc[h * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(dst + (uint32_t)(i0 / 8 + h) * 128u) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // out[b][i][j] = in[b][j][i] for 64x64 blocks (the STN's transform, transposed for the W1*T product)
 __global__ void transpose64_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -732,11 +765,9 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             // pass B: STN64 -> T
             launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st);
             fc_tail(f.stn2.c3, t.stn_fc[br], t.fc_on_tc, gmax, Bc, g, f1, f2, T, st);
-            launch_add_identity64(T, Bc, st);
-            // W1' = conv1.W * T  -> per-query fp16 operand images
-            P2S_LAUNCH(transpose64_kernel, (unsigned)cdiv(Bc * 4096, 256), 256, 0, st, T, Tt, Bc);
-            launch_gemm_nt(f.conv1.W, 0, 64, Tt, 4096, nullptr, T, 4096, 64, 64, 64, 64, (int)Bc, false, st);
-            P2S_LAUNCH(pack_perq_kernel, (unsigned)cdiv(Bc * 4096, 256), 256, 0, st, T, Bc, perq);
+            // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
+            P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq);
+            (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
             launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st);
             launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);

@@ -1,0 +1,105 @@
+"""GPU: the drop-in boundary -- the reference's entry points, file formats and output tree,
+on the analogue of BASELINE config 1 (full_eval plumbing: one shape, rand-init vanilla checkpoint, small grid)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2s_oracle as orc
+from points2surf_b200 import synth, mesh_io
+from points2surf_b200 import eval as p2s_eval
+from points2surf_b200 import sdf as p2s_sdf
+from points2surf_b200.model import PointsToSurfModel
+from helpers import load_golden, calibrated_state_dict, golden_model_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_dataset(tmp_path, variant='vanilla'):
+    g = load_golden('assembly.npz')
+    root = tmp_path / 'data'
+    (root / '04_pts').mkdir(parents=True)
+    np.save(root / '04_pts' / 'shape_a.xyz.npy', g['cloud'])
+    np.save(root / '04_pts' / 'shape_b.xyz.npy', np.concatenate([synth.make_cloud('torus', 4000, seed=3), np.zeros((4000, 2), np.float32)], 1))
+    (root / 'testset.txt').write_text('shape_a\nshape_b\n\n')
+    models = tmp_path / 'models'
+    models.mkdir()
+    sd = calibrated_state_dict(variant, 31)
+    torch.save({'module.' + k: v for k, v in sd.items()}, models / 'p2s_test_model.pth')     # DataParallel-style keys
+    torch.save(synth.make_train_opt(variant), models / 'p2s_test_params.pth')                  # pickled Namespace
+    return root, models, sd
+
+
+def test_full_eval_plumbing(tmp_path):
+    root, models, sd = _make_dataset(tmp_path)
+    out = tmp_path / 'results'
+    opt = p2s_eval.parse_arguments(['--indir', str(root), '--outdir', str(out), '--modeldir', str(models), '--models', 'p2s_test',
+                                    '--dataset', 'testset.txt', '--query_grid_resolution', '24', '--epsilon', '3',
+                                    '--certainty_threshold', '13', '--sigma', '5', '--batchSize', '501', '--workers', '0'])
+    assert opt.dataset == 'testset.txt' and opt.seed == 40938661
+    opt.reconstruction = True
+    p2s_eval.points_to_surf_eval(opt)
+    rec = out / 'rec'
+    for name, cloud in (('shape_a', load_golden('assembly.npz')['cloud']), ('shape_b', synth.make_cloud('torus', 4000, seed=3))):
+        q = np.load(rec / 'query_pts_ms' / (name + '.xyz.npy'))
+        d = np.load(rec / 'dist_ms' / (name + '.xyz.npy'))
+        assert np.array_equal(q, orc.query_grid(cloud, 24, 3))            # same query set and order as the reference
+        assert d.shape == (len(q),) and d.dtype == np.float32 and np.isfinite(d).all()
+        assert (d > 0).any() and (d < 0).any()
+        assert np.array_equal(np.load(rec / 'eval' / (name + '.xyz.npy')), d)
+        assert np.loadtxt(rec / 'eval' / (name + '.xyz.txt')).shape == d.shape
+        for sub in ('vis', 'query_pts_ms_vis'):
+            v, f = mesh_io.read_ply(str(rec / sub / (name + '.ply')))
+            assert v.shape == q.shape and len(f) == 0
+    # volume -> mesh stage (full_eval.py:56-62)
+    p2s_sdf.implicit_surface_to_mesh_directory(str(rec / 'dist_ms'), str(rec / 'query_pts_ms'), str(rec / 'vol'), str(rec / 'mesh'),
+                                               24, 5, 13, 0)
+    for name in ('shape_a', 'shape_b'):
+        assert (rec / 'vol' / (name + '.off')).read_text().startswith('COFF')
+        v, f = mesh_io.read_ply(str(rec / 'mesh' / (name + '.ply')))
+        assert len(v) > 0 and len(f) > 0 and f.max() < len(v) and np.abs(v).max() <= 1.0
+    # second call is a no-op (mtime rule of file_utils.call_necessary)
+    t0 = os.path.getmtime(rec / 'mesh' / 'shape_a.ply')
+    p2s_sdf.implicit_surface_to_mesh_directory(str(rec / 'dist_ms'), str(rec / 'query_pts_ms'), str(rec / 'vol'), str(rec / 'mesh'), 24, 5, 13, 0)
+    assert os.path.getmtime(rec / 'mesh' / 'shape_a.ply') == t0
+    # the non-reconstruction pass needs 05_query_pts; emulate it with a few grid points
+    (root / '05_query_pts').mkdir()
+    for name in ('shape_a', 'shape_b'):
+        np.save(root / '05_query_pts' / (name + '.ply.npy'), np.load(rec / 'query_pts_ms' / (name + '.xyz.npy'))[:50])
+    opt.reconstruction = False
+    p2s_eval.points_to_surf_eval(opt)
+    assert np.load(out / 'eval' / 'eval' / 'shape_a.xyz.npy').shape == (50,)
+
+
+def test_model_module_is_a_drop_in():
+    sd, inp, g = golden_model_case('vanilla')
+    m = PointsToSurfModel(net_size_max=1024, num_points=300, output_dim=2, use_point_stn=True, use_feat_stn=True, sym_op='max',
+                          use_query_point=True, sub_sample_size=1000, do_augmentation=False, single_transformer=0,
+                          shared_transformation=True, precision='fp32')
+    ref_keys = list(synth.make_state_dict('vanilla', 0).keys())
+    assert list(m.state_dict().keys()) == ref_keys
+    m.load_state_dict({'module.' + k: v for k, v in sd.items()})        # checkpoint saved from the DataParallel wrapper
+    m.eval()
+    x = {k: torch.from_numpy(v.copy()).cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        y = m(x)
+    assert np.abs(y.cpu().numpy() - g['logits']).max() < 2e-3
+    # like the reference, forward centres the caller's sub-sample in place (points_to_surf_model.py:303)
+    assert np.allclose(x['pts_sub_sample_ms'].cpu().numpy(), inp['pts_sub_sample_ms'] - inp['imp_surf_query_point_ms'][:, None, :], atol=1e-6)
+    with pytest.raises(ValueError):
+        PointsToSurfModel(sym_op='sum', output_dim=2)
+    with pytest.raises(ValueError):
+        PointsToSurfModel(single_transformer=True, output_dim=2)
+
+
+def test_unsupported_options_raise(tmp_path):
+    root, models, _ = _make_dataset(tmp_path)
+    opt_ns = synth.make_train_opt('vanilla')
+    opt_ns.patch_radius = 0.1
+    torch.save(opt_ns, models / 'p2s_test_params.pth')
+    opt = p2s_eval.parse_arguments(['--indir', str(root), '--outdir', str(tmp_path / 'r'), '--modeldir', str(models), '--models', 'p2s_test',
+                                    '--query_grid_resolution', '16', '--epsilon', '3'])
+    opt.reconstruction = True
+    with pytest.raises(ValueError):
+        p2s_eval.points_to_surf_eval(opt)
