@@ -17,6 +17,24 @@ void sdf_from_logits(const float* logits, const float* radius, int64_t B, float*
 void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res, int sigma, float thr, float* vol, int* iterations_host, cudaStream_t st);
 void marching_cubes(const float* vol, int res, float level, float* verts, int64_t vcap, int32_t* faces, int64_t fcap, int64_t* nverts_host, int64_t* nfaces_host, cudaStream_t st);
 
+}  // namespace p2s
+#include <chrono>
+#include <map>
+namespace p2s {
+static std::map<std::string, std::pair<double, long>> g_stage;
+bool StageTimer::enabled() { static int e = -1; if (e < 0) { const char* v = getenv("P2S_STAGE_TIMING"); e = (v && v[0] == '1') ? 1 : 0; } return e == 1; }
+void StageTimer::add(const char* label, double ms) { auto& x = g_stage[label]; x.first += ms; x.second += 1; }
+void StageTimer::report() {
+    if (!enabled() || g_stage.empty()) return;
+    double tot = 0; for (auto& kv : g_stage) tot += kv.second.first;
+    fprintf(stderr, "p2s stage timing (host wall clock, stream synchronised around each stage):\n");
+    for (auto& kv : g_stage) fprintf(stderr, "  %-28s %10.2f ms  %5.1f%%  (%ld calls)\n", kv.first.c_str(), kv.second.first, 100.0 * kv.second.first / tot, kv.second.second);
+    g_stage.clear();
+}
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+StageScope::StageScope(const char* l, cudaStream_t s) : label(l), st(s), on(StageTimer::enabled()) { if (on) { cudaStreamSynchronize(st); t0 = now_ms(); } }
+StageScope::~StageScope() { if (on) { cudaStreamSynchronize(st); StageTimer::add(label, now_ms() - t0); } }
+
 namespace {
 
 struct BlobCursor {
@@ -95,7 +113,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
     int64_t Qall = 0;
     const int64_t vox = (int64_t)rc.res * rc.res * rc.res;
     int32_t* all_idx = m.ws_misc.as<int32_t>((size_t)vox);   // worst case; candidate list of the whole shape
-    query_grid(pts, N, rc.res, rc.eps, all_idx, vox, &Qall, st);
+    { StageScope t("grid", st); query_grid(pts, N, rc.res, rc.eps, all_idx, vox, &Qall, st); }
     if (first_query < 0) first_query = 0;
     if (first_query > Qall) first_query = Qall;
     int64_t Q = (num_queries < 0) ? (Qall - first_query) : num_queries;
@@ -116,10 +134,11 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
     for (int64_t q0 = 0; q0 < Q; q0 += batch) {
         const int64_t n = (Q - q0 < batch) ? (Q - q0) : batch;
         query_points(lin_idx + q0, n, rc.res, b.qpts, st);
-        knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st);
+        { StageScope t("assemble: knn_patch", st); knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
         // the Philox stream is keyed by the query's rank in the whole ordered list -> independent of slabs/batches
-        subsample(pts, N, b.qpts, n, first_query + q0, S, rc.subsample_mode, rc.seed, b.sub_ids, st);
-        gather_points(pts, b.sub_ids, n * S, b.sub, st);
+        { StageScope t("assemble: subsample+gather", st);
+          subsample(pts, N, b.qpts, n, first_query + q0, S, rc.subsample_mode, rc.seed, b.sub_ids, st);
+          gather_points(pts, b.sub_ids, n * S, b.sub, st); }
         forward(m, b.patch, b.sub, b.qpts, n, b.logits, st);
         sdf_from_logits(b.logits, b.radius, n, sdf + q0, st);
     }
@@ -186,6 +205,7 @@ void p2s_model_destroy(p2s_model* mm) {
     if (!mm) return;
     Model* m = reinterpret_cast<Model*>(mm);
     cudaSetDevice(m->device);
+    StageTimer::report();
     tc_destroy(*m);
     if (m->blob) cudaFree(m->blob);
     if (m->guard_count_dev) cudaFree(m->guard_count_dev);

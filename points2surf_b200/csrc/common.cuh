@@ -63,6 +63,19 @@ static inline int guarded(F&& f) {
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Optional coarse stage timing (env P2S_STAGE_TIMING=1): synchronises the stream around every stage and
+// accumulates host wall-clock per label; printed by p2s_model_destroy.  Diagnostics only.
+struct StageTimer {
+    static bool enabled();
+    static void add(const char* label, double ms);
+    static void report();
+};
+struct StageScope {
+    const char* label; cudaStream_t st; double t0 = 0.0; bool on;
+    StageScope(const char* l, cudaStream_t s);
+    ~StageScope();
+};
+
 // grow-only device scratch buffer
 struct DevBuf {
     void* p = nullptr;

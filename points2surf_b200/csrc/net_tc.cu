@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         const uint32_t a_col = tmem + lane_base + kColA + (uint32_t)c * 32u;
         int cur_q = -1;
         float qx = 0.f, qy = 0.f, qz = 0.f;
-        auto fetch = [&](int it2, float& x, float& y, float& z) {
+        // loads only: the centring subtraction happens at the use site one tile later, so the loads stay in flight
+        auto fetch = [&](int it2, float& x, float& y, float& z, float& cx, float& cy, float& cz) {
             const int qi2 = it2 / tpq, tq2 = it2 - qi2 * tpq;
             const size_t q2 = (size_t)stream + (size_t)qi2 * nstreams;
             const int sgi = tq2 < p.seg[0].tiles ? 0 : 1;
@@ -288,10 +289,11 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             if (local >= sg.n) local = 0;                              // duplicate padding
             const float* src = sg.ptr + (q2 * sg.n + local) * 3;
             x = src[0]; y = src[1]; z = src[2];
-            if (sg.center) { x -= p.query[q2 * 3 + 0]; y -= p.query[q2 * 3 + 1]; z -= p.query[q2 * 3 + 2]; }
+            cx = cy = cz = 0.f;
+            if (sg.center) { cx = p.query[q2 * 3 + 0]; cy = p.query[q2 * 3 + 1]; cz = p.query[q2 * 3 + 2]; }
         };
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (c < ntiles) fetch(c, x, y, z);
+        float x = 0.f, y = 0.f, z = 0.f, pcx = 0.f, pcy = 0.f, pcz = 0.f;
+        if (c < ntiles) fetch(c, x, y, z, pcx, pcy, pcz);
         uint32_t round = 0;
         for (int it = c; it < ntiles; it += 2) {
             const int qi = it / tpq;
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             (void)qx; (void)qy; (void)qz;
             // ---- layer 0 (fp32 FMA): 3 -> 64, ReLU, fp16 pairs, stored as the A operand in TMEM
             {
+                x -= pcx; y -= pcy; z -= pcz;              // model.py:303
                 uint32_t v[32];
 #pragma unroll
                 for (int j4 = 0; j4 < 16; ++j4) {
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 mbar_arrive(&bars->a_ready[c]);
             }
             // prefetch this chain's next point while the mid layers run
-            if (it + 2 < ntiles) fetch(it + 2, x, y, z);
+            if (it + 2 < ntiles) fetch(it + 2, x, y, z, pcx, pcy, pcz);
             // ---- mid layers
             int boff = 0;
             for (int l = 0; l < p.num_mid; ++l, ++round) {
@@ -748,8 +751,8 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
         const float* Rq = nullptr;
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
-            launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st);
-            fc_tail(m.point_stn.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st);
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st); }
+            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st); }
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
@@ -763,16 +766,17 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
-            launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st);
-            fc_tail(f.stn2.c3, t.stn_fc[br], t.fc_on_tc, gmax, Bc, g, f1, f2, T, st);
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st); }
+            { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], t.fc_on_tc, gmax, Bc, g, f1, f2, T, st); }
             // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
-            P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq);
+            { StageScope ts("net: fold W1*T", st); P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq); }
             (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
-            launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st);
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st); }
             launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
+        StageScope ts_head("net: fc tails", st);
         run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, t.fc_on_tc, st);
         run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, t.fc_on_tc, st);
         run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, t.fc_on_tc, st);
@@ -782,6 +786,7 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
 
     // guard band: queries whose sign logit is too close to 0 for fp16-operand arithmetic are recomputed in fp32
     if (m.guard_band > 0.f) {
+        StageScope ts_guard("net: guard-band fp32 recompute", st);
         int32_t* list = m.ws_guard.as<int32_t>((size_t)B + 64);
         int* count = reinterpret_cast<int*>(list + B);
         P2S_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));

@@ -99,6 +99,8 @@ def read_ply(file_path):
         else:
             assert fmt == 'binary_little_endian', fmt
             for el in elems:
+                if el['count'] == 0:
+                    continue
                 if el['name'] == 'vertex':
                     dt = np.dtype([(p[-1], '<' + tmap[p[0]]) for p in el['props']])
                     rec = np.frombuffer(fp.read(dt.itemsize * el['count']), dtype=dt)

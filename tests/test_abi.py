@@ -61,3 +61,18 @@ def test_no_cpu_fallback():
         ops.Engine(synth.make_state_dict('max', 0), 0, 0)
     with pytest.raises(_lib.P2SError):
         ops.query_grid(torch.zeros(10, 3), 16, 3)
+
+
+def test_ply_off_roundtrip(tmp_path):
+    from points2surf_b200 import mesh_io
+    v = np.random.RandomState(0).rand(7, 3).astype(np.float32)
+    f = np.array([[0, 1, 2], [2, 3, 4], [4, 5, 6]], np.int32)
+    mesh_io.write_ply(str(tmp_path / 'm.ply'), v, f)
+    v2, f2 = mesh_io.read_ply(str(tmp_path / 'm.ply'))
+    assert np.array_equal(v, v2) and np.array_equal(f, f2)
+    mesh_io.write_ply(str(tmp_path / 'p.ply'), v, None, colors=np.random.rand(7, 3))
+    v3, f3 = mesh_io.read_ply(str(tmp_path / 'p.ply'))
+    assert np.array_equal(v, v3) and len(f3) == 0
+    mesh_io.write_off(str(tmp_path / 'q.off'), v, np.array([]), colors_vertex=np.random.rand(7, 3))
+    lines = (tmp_path / 'q.off').read_text().split('\n')
+    assert lines[0] == 'COFF' and lines[1] == '7 0 0' and len(lines[2].split()) == 6
