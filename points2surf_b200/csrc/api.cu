@@ -10,7 +10,9 @@ std::atomic<uint64_t> g_launches{0};
 void query_grid(const float* pts, int64_t N, int res, int eps, int32_t* lin_idx, int64_t cap, int64_t* count_host, cudaStream_t st);
 void query_points(const int32_t* lin_idx, int64_t Q, int res, float* out, cudaStream_t st);
 void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids, float* patch, float* radius, cudaStream_t st);
-void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st);
+void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr);
+void gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
+void scatter_f32(const float* src, const int32_t* idx, int64_t n, float* dst, cudaStream_t st);
 void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st);
 int assemble_error_check(cudaStream_t st);
 void sdf_from_logits(const float* logits, const float* radius, int64_t B, float* sdf, cudaStream_t st);
@@ -112,7 +114,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
     int64_t Qall = 0;
     const int64_t vox = (int64_t)rc.res * rc.res * rc.res;
-    int32_t* all_idx = m.ws_misc.as<int32_t>((size_t)vox);   // worst case; candidate list of the whole shape
+    int32_t* all_idx = m.ws_misc.as<int32_t>((size_t)vox + 2 * 16384 + 64);   // worst case candidate list (+ guard scratch behind it)
     { StageScope t("grid", st); query_grid(pts, N, rc.res, rc.eps, all_idx, vox, &Qall, st); }
     if (first_query < 0) first_query = 0;
     if (first_query > Qall) first_query = Qall;
@@ -131,16 +133,55 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
     auto take = [&](size_t n) { float* r = p; p += (n * (size_t)batch + 3) / 4 * 4; return r; };
     b.qpts = take(3); b.patch = take((size_t)P * 3); b.radius = take(1); b.sub = take((size_t)S * 3); b.logits = take(2);
     b.sub_ids = reinterpret_cast<int32_t*>(take((size_t)S));
-    for (int64_t q0 = 0; q0 < Q; q0 += batch) {
-        const int64_t n = (Q - q0 < batch) ? (Q - q0) : batch;
-        query_points(lin_idx + q0, n, rc.res, b.qpts, st);
+    // guard band of the tensor-core path: flagged queries are collected over the whole slab and recomputed on the
+    // fp32 path in one batch at the end (large GEMMs instead of ~80-query slivers per batch)
+    const bool defer_guard = (m.precision == P2S_PRECISION_TC) && (m.guard_band > 0.f);
+    int32_t* glist = nullptr;
+    int* gcount = nullptr;
+    if (defer_guard) {
+        glist = m.ws_guard.as<int32_t>((size_t)Q + 64);
+        gcount = reinterpret_cast<int*>(glist + Q);
+        P2S_CUDA(cudaMemsetAsync(gcount, 0, sizeof(int), st));
+        m.guard_list = glist; m.guard_list_count = gcount; m.guard_list_cap = Q;
+    }
+    auto assemble = [&](const int32_t* lin, int64_t n, int64_t qbase, const int32_t* qidx) {
+        query_points(lin, n, rc.res, b.qpts, st);
         { StageScope t("assemble: knn_patch", st); knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
         // the Philox stream is keyed by the query's rank in the whole ordered list -> independent of slabs/batches
         { StageScope t("assemble: subsample+gather", st);
-          subsample(pts, N, b.qpts, n, first_query + q0, S, rc.subsample_mode, rc.seed, b.sub_ids, st);
+          subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx);
           gather_points(pts, b.sub_ids, n * S, b.sub, st); }
-        forward(m, b.patch, b.sub, b.qpts, n, b.logits, st);
-        sdf_from_logits(b.logits, b.radius, n, sdf + q0, st);
+    };
+    try {
+        for (int64_t q0 = 0; q0 < Q; q0 += batch) {
+            const int64_t n = (Q - q0 < batch) ? (Q - q0) : batch;
+            assemble(lin_idx + q0, n, first_query + q0, nullptr);
+            m.guard_base = q0;
+            forward(m, b.patch, b.sub, b.qpts, n, b.logits, st);
+            sdf_from_logits(b.logits, b.radius, n, sdf + q0, st);
+        }
+        if (defer_guard) {
+            m.guard_list = nullptr;
+            int ng = 0;
+            P2S_CUDA(cudaMemcpyAsync(&ng, gcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+            P2S_CUDA(cudaStreamSynchronize(st));
+            if (ng > Q) ng = (int)Q;
+            m.last_guard_count += ng;
+            StageScope tg("net: guard-band fp32 recompute", st);
+            int32_t* glin = reinterpret_cast<int32_t*>(m.ws_misc.as<float>((size_t)vox + (size_t)batch * 2 + 64) + vox);   // behind all_idx
+            float* gsdf = reinterpret_cast<float*>(glin + batch);
+            for (int64_t g0 = 0; g0 < ng; g0 += batch) {
+                const int64_t n = (ng - g0 < batch) ? (ng - g0) : batch;
+                gather_i32(lin_idx, glist + g0, n, glin, st);
+                assemble(glin, n, first_query, glist + g0);
+                forward_fp32(m, b.patch, b.sub, b.qpts, n, b.logits, st);
+                sdf_from_logits(b.logits, b.radius, n, gsdf, st);
+                scatter_f32(gsdf, glist + g0, n, sdf, st);
+            }
+        }
+    } catch (...) {
+        m.guard_list = nullptr;
+        throw;
     }
     int err = assemble_error_check(st);
     P2S_CHECK(err == 0, "degenerate cloud: more than 512 points tie at a selection boundary");

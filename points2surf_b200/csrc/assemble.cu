@@ -216,14 +216,14 @@ __device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1]
     return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
-__global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, int S, uint64_t seed, int32_t* __restrict__ out) {
+__global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, const int32_t* __restrict__ qidx, int S, uint64_t seed, int32_t* __restrict__ out) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int quads = (S + 3) / 4;
     if (t >= Q * quads) return;
     int64_t q = t / quads;
     int j4 = (int)(t % quads);
     uint32_t r[4];
-    uint64_t qi = (uint64_t)(qbase + q);
+    uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
     philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)j4, 0x5ab5a3e1u, r);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -237,7 +237,7 @@ __global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, int S,
 template <bool CACHE>
 __global__ void __launch_bounds__(kThreads)
 subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries,
-                          int64_t qbase, int S, uint64_t seed, int32_t* __restrict__ out, int* __restrict__ err_flag) {
+                          int64_t qbase, const int32_t* __restrict__ qidx, int S, uint64_t seed, int32_t* __restrict__ out, int* __restrict__ err_flag) {
     extern __shared__ float s_key[];     // [N] when CACHE
     __shared__ SelectSmem s;
     __shared__ float red[kThreads / 32];
@@ -263,7 +263,7 @@ subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __r
     }
     __syncthreads();
     dmax = s_dmax;
-    const uint64_t qi = (uint64_t)(qbase + q);
+    const uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
     // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
     auto clock_of = [&](float d, uint32_t rnd) {
         float dn = __fdiv_rn(d, dmax);
@@ -354,14 +354,15 @@ void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int
     P2S_LAUNCH(knn_patch_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, k, ids, patch, radius, err_flag_dev());
 }
 
+// the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q)
 void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S,
-               int mode, uint64_t seed, int32_t* out, cudaStream_t st) {
+               int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx) {
     P2S_CHECK(N >= S, "sub-sample needs N >= sub_sample_size (reference zero-pads after an in-place shuffle; unsupported)");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
     if (mode == P2S_SUBSAMPLE_UNIFORM) {
         int64_t threads = Q * ((S + 3) / 4);
-        P2S_LAUNCH(subsample_uniform_kernel, (unsigned)cdiv(threads, 256), 256, 0, st, (int)N, Q, qbase, S, seed, out);
+        P2S_LAUNCH(subsample_uniform_kernel, (unsigned)cdiv(threads, 256), 256, 0, st, (int)N, Q, qbase, qidx, S, seed, out);
     } else if (mode == P2S_SUBSAMPLE_WEIGHTED) {
         const size_t cache_bytes = (size_t)N * sizeof(float);
         if (cache_bytes <= 160 * 1024) {
@@ -370,13 +371,28 @@ void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int
                 P2S_CUDA(cudaFuncSetAttribute(subsample_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                 attr_set = true;
             }
-            P2S_LAUNCH(subsample_weighted_kernel<true>, (unsigned)Q, kThreads, cache_bytes, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+            P2S_LAUNCH(subsample_weighted_kernel<true>, (unsigned)Q, kThreads, cache_bytes, st, pts, (int)N, queries, qbase, qidx, S, seed, out, err_flag_dev());
         } else {
-            P2S_LAUNCH(subsample_weighted_kernel<false>, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, S, seed, out, err_flag_dev());
+            P2S_LAUNCH(subsample_weighted_kernel<false>, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, qidx, S, seed, out, err_flag_dev());
         }
     } else {
         throw Error("unknown sub-sample mode");
     }
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void scatter_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, float* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = src[i];
+}
+void gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, cudaStream_t st) {
+    if (n > 0) P2S_LAUNCH(gather_i32_kernel, (unsigned)cdiv(n, 256), 256, 0, st, src, idx, n, dst);
+}
+void scatter_f32(const float* src, const int32_t* idx, int64_t n, float* dst, cudaStream_t st) {
+    if (n > 0) P2S_LAUNCH(scatter_f32_kernel, (unsigned)cdiv(n, 256), 256, 0, st, src, idx, n, dst);
 }
 
 void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st) {

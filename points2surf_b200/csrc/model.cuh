@@ -44,6 +44,12 @@ struct Model {
     DevBuf ws_host;                      // device staging of host-call inputs/outputs
     int64_t* guard_count_dev = nullptr;
     int64_t last_guard_count = 0;
+    // deferred guard band (fused pipeline): instead of recomputing inside every batch, forward_tc appends
+    // guard_base + i for every flagged query to guard_list; the caller recomputes them all at once
+    int32_t* guard_list = nullptr;
+    int* guard_list_count = nullptr;
+    int64_t guard_list_cap = 0;
+    int64_t guard_base = 0;
     float* debug_aux = nullptr;          // optional [B][kAuxStride]: R(9), feat_local_max(1024), feat_global_max(1024)
 };
 constexpr int kAuxStride = 2064;

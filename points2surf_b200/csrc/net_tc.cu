@@ -468,7 +468,7 @@ __global__ void pack_perq_kernel(const float* __restrict__ W, int64_t B, uint8_t
 // viewed as [64][64] (model.py:66-68,196,201).  One CTA per query, 256 threads, W1 and T staged in shared memory.
 __global__ void __launch_bounds__(256) fold_w1_kernel(const float* __restrict__ W1, const float* __restrict__ T, int64_t B, uint8_t* __restrict__ img) {
     __shared__ float sW[64][65];
-    __shared__ float sT[64][65];
+    __shared__ __align__(16) float sT[64][68];
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
     for (int e = tid; e < 4096; e += 256) {
@@ -485,7 +485,13 @@ __global__ void __launch_bounds__(256) fold_w1_kernel(const float* __restrict__ 
     for (int j = 0; j < 64; ++j) {
         const float w = sW[o][j];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fmaf(w, sT[j][i0 + i], acc[i]);
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&sT[j][i0 + 4 * i4]);
+            acc[4 * i4 + 0] = fmaf(w, t4.x, acc[4 * i4 + 0]);
+            acc[4 * i4 + 1] = fmaf(w, t4.y, acc[4 * i4 + 1]);
+            acc[4 * i4 + 2] = fmaf(w, t4.z, acc[4 * i4 + 2]);
+            acc[4 * i4 + 3] = fmaf(w, t4.w, acc[4 * i4 + 3]);
+        }
     }
     uint8_t* dst = img + b * 8192 + (uint32_t)(o >> 3) * 1024u + (uint32_t)(o & 7) * 16u;
 #pragma unroll
@@ -506,10 +512,13 @@ __global__ void transpose64_kernel(const float* __restrict__ in, float* __restri
     out[e] = in[b * 4096 + j * 64 + i];
 }
 
-__global__ void guard_flag_kernel(const float* __restrict__ logits, int64_t B, float band, int32_t* __restrict__ list, int* __restrict__ count) {
+__global__ void guard_flag_kernel(const float* __restrict__ logits, int64_t B, float band, int32_t* __restrict__ list, int* __restrict__ count, int64_t base, int64_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    if (fabsf(logits[i * 2 + 1]) < band) list[atomicAdd(count, 1)] = (int32_t)i;
+    if (fabsf(logits[i * 2 + 1]) < band) {
+        int slot = atomicAdd(count, 1);
+        if (slot < cap) list[slot] = (int32_t)(base + i);
+    }
 }
 __global__ void guard_gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ list, int n, int row_floats, float* __restrict__ dst) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -785,12 +794,15 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
     }
 
     // guard band: queries whose sign logit is too close to 0 for fp16-operand arithmetic are recomputed in fp32
-    if (m.guard_band > 0.f) {
+    if (m.guard_band > 0.f && m.guard_list) {
+        // deferred: only record which queries fall into the band (the fused pipeline recomputes them in one batch)
+        P2S_LAUNCH(guard_flag_kernel, (unsigned)cdiv(B, 256), 256, 0, st, logits, B, m.guard_band, m.guard_list, m.guard_list_count, m.guard_base, m.guard_list_cap);
+    } else if (m.guard_band > 0.f) {
         StageScope ts_guard("net: guard-band fp32 recompute", st);
         int32_t* list = m.ws_guard.as<int32_t>((size_t)B + 64);
         int* count = reinterpret_cast<int*>(list + B);
         P2S_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
-        P2S_LAUNCH(guard_flag_kernel, (unsigned)cdiv(B, 256), 256, 0, st, logits, B, m.guard_band, list, count);
+        P2S_LAUNCH(guard_flag_kernel, (unsigned)cdiv(B, 256), 256, 0, st, logits, B, m.guard_band, list, count, (int64_t)0, B);
         int n = 0;
         P2S_CUDA(cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, st));
         P2S_CUDA(cudaStreamSynchronize(st));
