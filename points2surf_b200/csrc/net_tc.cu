@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const float4 wy = *reinterpret_cast<const float4*>(wq + 1 * 64 + 4 * j4);
                     const float4 wz = *reinterpret_cast<const float4*>(wq + 2 * 64 + 4 * j4);
                     const float4 bb = *reinterpret_cast<const float4*>(s_b0 + 4 * j4);
-                    float h0 = fmaf(wx.x, x, fmaf(wy.x, y, fmaf(wz.x, z, bb.x)));
-                    float h1 = fmaf(wx.y, x, fmaf(wy.y, y, fmaf(wz.y, z, bb.y)));
-                    float h2 = fmaf(wx.z, x, fmaf(wy.z, y, fmaf(wz.z, z, bb.z)));
-                    float h3 = fmaf(wx.w, x, fmaf(wy.w, y, fmaf(wz.w, z, bb.w)));
-                    v[2 * j4] = pack_relu(h0, h1);
-                    v[2 * j4 + 1] = pack_relu(h2, h3);
+                    // same association as the scalar form fma(wx, x, fma(wy, y, fma(wz, z, b))), two channels per FFMA2
+                    const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z);
+                    const float2 h01 = ffma2(make_float2(wx.x, wx.y), xx, ffma2(make_float2(wy.x, wy.y), yy, ffma2(make_float2(wz.x, wz.y), zz, make_float2(bb.x, bb.y))));
+                    const float2 h23 = ffma2(make_float2(wx.z, wx.w), xx, ffma2(make_float2(wy.z, wy.w), yy, ffma2(make_float2(wz.z, wz.w), zz, make_float2(bb.z, bb.w))));
+                    v[2 * j4] = pack_relu(h01.x, h01.y);
+                    v[2 * j4 + 1] = pack_relu(h23.x, h23.y);
                 }
                 tmem_st_x32(a_col, v);
                 tmem_st_wait();
@@ -363,8 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bb = *reinterpret_cast<const float4*>(s_bias + boff + n0 + 4 * j4);
-                        v[2 * j4] = pack_relu(__uint_as_float(r[4 * j4]) + bb.x, __uint_as_float(r[4 * j4 + 1]) + bb.y);
-                        v[2 * j4 + 1] = pack_relu(__uint_as_float(r[4 * j4 + 2]) + bb.z, __uint_as_float(r[4 * j4 + 3]) + bb.w);
+                        const float2 s01 = fadd2(make_float2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), make_float2(bb.x, bb.y));
+                        const float2 s23 = fadd2(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), make_float2(bb.z, bb.w));
+                        v[2 * j4] = pack_relu(s01.x, s01.y);
+                        v[2 * j4 + 1] = pack_relu(s23.x, s23.y);
                     }
                     if (!last) {
                         // next layer's A operand (K index = channel, columns hold channel pairs); the MMA that read
