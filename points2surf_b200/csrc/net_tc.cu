@@ -16,9 +16,10 @@
 // a per-thread reduction over TMEM columns (no shuffles).  Each CTA owns 512 of the 1024 channels (its half
 // of W3, 128 KB fp16, stays resident in shared memory); CTA 2j and 2j+1 stream the same queries.
 //
-// Warp roles (448 threads): warps 0-3 and 9-12 are two chains (even / odd tiles) doing the first layer and the
-// mid-layer epilogues (thread = point = TMEM lane), warps 4-7 the column-max epilogue of the big layer, warp 8
-// issues the big-layer MMAs (blocking waits), warp 13 the mid-layer MMAs of both chains (polling).
+// Warp roles (576 threads): warps 14-17 compute the first layer (fp32 FMA) of every tile; warps 0-3 and 9-12 are two
+// chains (even / odd tiles) running the mid-layer epilogues (thread = point = TMEM lane); warps 4-7 the column-max
+// epilogue of the big layer; warp 8 issues the big-layer MMAs (blocking waits), warp 13 the mid-layer MMAs of both
+// chains (polling).
 //
 // The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
 #include "model.cuh"
@@ -35,7 +36,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kThreads = 448;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer
+constexpr int kThreads = 576;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer | 14-17 first layer
 // shared memory map (bytes)
 constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
 constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
@@ -44,7 +45,7 @@ constexpr uint32_t kOffW3 = 0;
 constexpr uint32_t kOffMid = kOffW3 + kW3Bytes;
 constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
 constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;
-constexpr uint32_t kSmallBytes = 2 * 192 * 4 + 320 * 4 + 152;  // Wq[2 chains][3][64], biases[256 mid + 64 first], barriers
+constexpr uint32_t kSmallBytes = 192 * 4 + 320 * 4 + 168;  // Wq[3][64], biases[256 mid + 64 first], barriers
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM map (columns)
@@ -81,11 +82,11 @@ struct PassParams {
 struct Bars {
     uint64_t w_full, wq_full, perq_done;
     uint64_t dmid_free[2];      // [0]: 128-column accumulator, [1]: 64-column accumulator
-    uint64_t a_ready[2], dmid_ready[2];
+    uint64_t a_ready[2], a_free[2], dmid_ready[2];
     uint64_t act2_full[2], act2_empty[2], d3_full[2], d3_empty[2];
     uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 152, "barrier block");
+static_assert(sizeof(Bars) <= 168, "barrier block");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 #if P2S_TC_BOUNDED_WAIT
@@ -111,7 +112,7 @@ __device__ __forceinline__ uint32_t pack_relu(float a, float b) {
 __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [2][3][64]: rows of (W0*R)^T per chain
-    float* s_bias = s_wq + 2 * 192;                                       // [256] mid biases back to back, [64] first-layer bias
+    float* s_bias = s_wq + 192;                                           // [256] mid biases back to back, [64] first-layer bias
     Bars* bars = reinterpret_cast<Bars*>(s_bias + 320);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = blockIdx.x & 1;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         mbar_init(&bars->dmid_free[1], 128);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->a_ready[i], 128);
+            mbar_init(&bars->a_free[i], 128);
             mbar_init(&bars->dmid_ready[i], 1);
             mbar_init(&bars->act2_full[i], 128);
             mbar_init(&bars->act2_empty[i], 1);
@@ -268,81 +270,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             }
         }
     } else if (warp < 4 || (warp >= 9 && warp < 13)) {
-        // =============================================================== first layer + mid-layer epilogues (two chains)
+        // =============================================================== mid-layer epilogues (two chains)
         const int c = (warp < 4) ? 0 : 1;                 // chain c owns tiles c, c+2, ...; act2 buffer c; A columns c
         const int grp = warp & 3;                         // TMEM lane quarter this warp may access
         const int pt = grp * 32 + lane;                   // point (row) of the tile handled by this thread
-        const int ct = (warp < 4) ? tid : (tid - 9 * 32); // thread index inside the chain's warpgroup
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
-        float* wq = s_wq + c * 192;
-        const float* s_b0 = s_bias + 256;
         const uint32_t a_col = tmem + lane_base + kColA + (uint32_t)c * 32u;
-        int cur_q = -1;
-        float qx = 0.f, qy = 0.f, qz = 0.f;
-        // loads only: the centring subtraction happens at the use site one tile later, so the loads stay in flight
-        auto fetch = [&](int it2, float& x, float& y, float& z, float& cx, float& cy, float& cz) {
-            const int qi2 = it2 / tpq, tq2 = it2 - qi2 * tpq;
-            const size_t q2 = (size_t)stream + (size_t)qi2 * nstreams;
-            const int sgi = tq2 < p.seg[0].tiles ? 0 : 1;
-            const Seg& sg = p.seg[sgi];
-            int local = (tq2 - (sgi ? p.seg[0].tiles : 0)) * kTile + pt;
-            if (local >= sg.n) local = 0;                              // duplicate padding
-            const float* src = sg.ptr + (q2 * sg.n + local) * 3;
-            x = src[0]; y = src[1]; z = src[2];
-            cx = cy = cz = 0.f;
-            if (sg.center) { cx = p.query[q2 * 3 + 0]; cy = p.query[q2 * 3 + 1]; cz = p.query[q2 * 3 + 2]; }
-        };
-        float x = 0.f, y = 0.f, z = 0.f, pcx = 0.f, pcy = 0.f, pcz = 0.f;
-        if (c < ntiles) fetch(c, x, y, z, pcx, pcy, pcz);
         uint32_t round = 0;
         for (int it = c; it < ntiles; it += 2) {
-            const int qi = it / tpq;
-            if (qi != cur_q) {
-                // (W0 * R)^T for this query -> this chain's smem copy
-                const size_t q = (size_t)stream + (size_t)qi * nstreams;
-                if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (ct < 64) {
-                    float w0 = p.W0[ct * 3 + 0], w1 = p.W0[ct * 3 + 1], w2 = p.W0[ct * 3 + 2];
-                    float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-                    if (p.R) {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) r[i] = p.R[q * 9 + i];
-                    }
-                    wq[0 * 64 + ct] = w0 * r[0] + w1 * r[3] + w2 * r[6];
-                    wq[1 * 64 + ct] = w0 * r[1] + w1 * r[4] + w2 * r[7];
-                    wq[2 * 64 + ct] = w0 * r[2] + w1 * r[5] + w2 * r[8];
-                }
-                if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-                cur_q = qi;
-            }
-            (void)qx; (void)qy; (void)qz;
-            // ---- layer 0 (fp32 FMA): 3 -> 64, ReLU, fp16 pairs, stored as the A operand in TMEM
-            {
-                x -= pcx; y -= pcy; z -= pcz;              // model.py:303
-                uint32_t v[32];
-#pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4) {
-                    const float4 wx = *reinterpret_cast<const float4*>(wq + 0 * 64 + 4 * j4);
-                    const float4 wy = *reinterpret_cast<const float4*>(wq + 1 * 64 + 4 * j4);
-                    const float4 wz = *reinterpret_cast<const float4*>(wq + 2 * 64 + 4 * j4);
-                    const float4 bb = *reinterpret_cast<const float4*>(s_b0 + 4 * j4);
-                    // same association as the scalar form fma(wx, x, fma(wy, y, fma(wz, z, b))), two channels per FFMA2
-                    const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z);
-                    const float2 h01 = ffma2(make_float2(wx.x, wx.y), xx, ffma2(make_float2(wy.x, wy.y), yy, ffma2(make_float2(wz.x, wz.y), zz, make_float2(bb.x, bb.y))));
-                    const float2 h23 = ffma2(make_float2(wx.z, wx.w), xx, ffma2(make_float2(wy.z, wy.w), yy, ffma2(make_float2(wz.z, wz.w), zz, make_float2(bb.z, bb.w))));
-                    v[2 * j4] = pack_relu(h01.x, h01.y);
-                    v[2 * j4 + 1] = pack_relu(h23.x, h23.y);
-                }
-                tmem_st_x32(a_col, v);
-                tmem_st_wait();
-                // never hold the shared D_mid accumulator while waiting for the big layer: the wait for this chain's
-                // act2 buffer happens BEFORE the MMA of the last mid layer is triggered
-                if (p.num_mid == 1) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
-                tc_fence_before();
-                mbar_arrive(&bars->a_ready[c]);
-            }
-            // prefetch this chain's next point while the mid layers run
-            if (it + 2 < ntiles) fetch(it + 2, x, y, z, pcx, pcy, pcz);
             // ---- mid layers
             int boff = 0;
             for (int l = 0; l < p.num_mid; ++l, ++round) {
@@ -350,6 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 tc_fence_after();
                 const int N = p.mid_N[l];
                 const bool last = (l == p.num_mid - 1);
+                if (last) {                         // every MMA that reads this chain's A columns has completed:
+                    tc_fence_before();              // the first-layer warps may write the next tile's operand
+                    mbar_arrive(&bars->a_free[c]);
+                }
                 const uint32_t dcol = (N == 64) ? kColDmidB : kColDmid;
                 for (int n0 = 0; n0 < N; n0 += 32) {
                     uint32_t r[32];
@@ -398,6 +337,79 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
                 boff += N;
             }
+        }
+    } else if (warp >= 14) {
+        // =============================================================== first layer (fp32 FMA) for both chains
+        // thread = point = TMEM lane; produces the K = 64 fp16 A operand of the first mid layer of tile `it` in the
+        // A columns of chain it & 1 as soon as that chain has released them.
+        const int grp = warp & 3;
+        const int pt = grp * 32 + lane;
+        const int ct = tid - 14 * 32;
+        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        float* wq = s_wq;
+        const float* s_b0 = s_bias + 256;
+        int cur_q = -1;
+        // loads only: the centring subtraction happens at the use site one tile later, so the loads stay in flight
+        auto fetch = [&](int it2, float& x, float& y, float& z, float& cx, float& cy, float& cz) {
+            const int qi2 = it2 / tpq, tq2 = it2 - qi2 * tpq;
+            const size_t q2 = (size_t)stream + (size_t)qi2 * nstreams;
+            const int sgi = tq2 < p.seg[0].tiles ? 0 : 1;
+            const Seg& sg = p.seg[sgi];
+            int local = (tq2 - (sgi ? p.seg[0].tiles : 0)) * kTile + pt;
+            if (local >= sg.n) local = 0;                              // duplicate padding
+            const float* src = sg.ptr + (q2 * sg.n + local) * 3;
+            x = src[0]; y = src[1]; z = src[2];
+            cx = cy = cz = 0.f;
+            if (sg.center) { cx = p.query[q2 * 3 + 0]; cy = p.query[q2 * 3 + 1]; cz = p.query[q2 * 3 + 2]; }
+        };
+        float x = 0.f, y = 0.f, z = 0.f, pcx = 0.f, pcy = 0.f, pcz = 0.f;
+        if (ntiles > 0) fetch(0, x, y, z, pcx, pcy, pcz);
+        for (int it = 0; it < ntiles; ++it) {
+            const int c = it & 1;
+            const int qi = it / tpq;
+            if (qi != cur_q) {
+                // (W0 * R)^T for this query
+                const size_t q = (size_t)stream + (size_t)qi * nstreams;
+                asm volatile("bar.sync 3, 128;" ::: "memory");      // readers of the previous query's copy are done
+                if (ct < 64) {
+                    float w0 = p.W0[ct * 3 + 0], w1 = p.W0[ct * 3 + 1], w2 = p.W0[ct * 3 + 2];
+                    float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+                    if (p.R) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) r[i] = p.R[q * 9 + i];
+                    }
+                    wq[0 * 64 + ct] = w0 * r[0] + w1 * r[3] + w2 * r[6];
+                    wq[1 * 64 + ct] = w0 * r[1] + w1 * r[4] + w2 * r[7];
+                    wq[2 * 64 + ct] = w0 * r[2] + w1 * r[5] + w2 * r[8];
+                }
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                cur_q = qi;
+            }
+            x -= pcx; y -= pcy; z -= pcz;              // model.py:303
+            uint32_t v[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 wx = *reinterpret_cast<const float4*>(wq + 0 * 64 + 4 * j4);
+                const float4 wy = *reinterpret_cast<const float4*>(wq + 1 * 64 + 4 * j4);
+                const float4 wz = *reinterpret_cast<const float4*>(wq + 2 * 64 + 4 * j4);
+                const float4 bb = *reinterpret_cast<const float4*>(s_b0 + 4 * j4);
+                // same association as the scalar form fma(wx, x, fma(wy, y, fma(wz, z, b))), two channels per FFMA2
+                const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z);
+                const float2 h01 = ffma2(make_float2(wx.x, wx.y), xx, ffma2(make_float2(wy.x, wy.y), yy, ffma2(make_float2(wz.x, wz.y), zz, make_float2(bb.x, bb.y))));
+                const float2 h23 = ffma2(make_float2(wx.z, wx.w), xx, ffma2(make_float2(wy.z, wy.w), yy, ffma2(make_float2(wz.z, wz.w), zz, make_float2(bb.z, bb.w))));
+                v[2 * j4] = pack_relu(h01.x, h01.y);
+                v[2 * j4 + 1] = pack_relu(h23.x, h23.y);
+            }
+            if (it + 1 < ntiles) fetch(it + 1, x, y, z, pcx, pcy, pcz);     // next tile's point, in flight during the store
+            wait_bar(&bars->a_free[c], (((uint32_t)it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * 32u, v);
+            tmem_st_wait();
+            // never trigger the last mid layer's MMA before this chain's act2 buffer is free: its epilogue must not
+            // hold the shared D_mid accumulator while waiting for the big layer
+            if (p.num_mid == 1) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
+            tc_fence_before();
+            mbar_arrive(&bars->a_ready[c]);
         }
     } else {
         // =============================================================== big-layer epilogue: max over the tile's points
