@@ -34,7 +34,7 @@ struct FcBars {
 
 __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A, int lda, const uint8_t* __restrict__ Wimg,
                                                     const float* __restrict__ bias, float* __restrict__ C, int ldc,
-                                                    int M, int N, int K, int relu) {
+                                                    int M, int N, int K, int relu, int pack_img) {
     extern __shared__ __align__(1024) uint8_t smem[];
     FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -93,7 +93,21 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             uint32_t r[32];
             tmem_ld_x32(tmem + lane_base + n0, r);
             tmem_ld_wait();
-            if (row < M) {
+            if (row < M && pack_img) {
+                // C is a per-row fp16 operand image of a [64][64] matrix (row-major index = column of this GEMM):
+                // K-major, LBO 128, SBO 1024 -- the per-query B operand of the pass kernel
+                uint8_t* img = reinterpret_cast<uint8_t*>(C) + (size_t)row * 8192;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const int col = nt * 128 + n0 + j;
+                    const int o = col >> 6, i = col & 63;
+                    uint32_t v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        v[e] = pack_half2(__uint_as_float(r[j + 2 * e]) + b[n0 + j + 2 * e], __uint_as_float(r[j + 2 * e + 1]) + b[n0 + j + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(img + (uint32_t)(o >> 3) * 1024u + (uint32_t)(i >> 3) * 128u + (uint32_t)(o & 7) * 16u) = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+            } else if (row < M) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
@@ -194,11 +208,21 @@ void fc_tc_init() {
 }
 
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
-                  int64_t M, int N, int K, bool relu, cudaStream_t st) {
+                  int64_t M, int N, int K, bool relu, cudaStream_t st, bool pack_img) {
     if (M <= 0) return;
-    P2S_CHECK(fc_tc_supported(N, K) && lda % 4 == 0 && ldc % 4 == 0, "bad FC shape for the tensor-core kernel");
+    P2S_CHECK(fc_tc_supported(N, K) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
     dim3 grid((unsigned)cdiv(M, 128), (unsigned)(N / 128), 1);
-    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img ? 1 : 0);
+}
+
+// images of a raw fp32 matrix W[N][K] (device pointer)
+uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs) {
+    P2S_CHECK(fc_tc_supported(N, K), "layer shape not supported by the tensor-core FC kernel");
+    void* p = nullptr;
+    P2S_CUDA(cudaMalloc(&p, (size_t)N * K * 4));
+    allocs.push_back(p);
+    P2S_LAUNCH(pack_fc_kernel, (unsigned)cdiv((int64_t)N * K, 256), 256, 0, 0, W, N, K, (uint8_t*)p);
+    return (uint8_t*)p;
 }
 
 }  // namespace p2s

@@ -70,7 +70,8 @@ bool fc_tc_supported(int N, int K);
 uint8_t* fc_tc_pack(const Layer& L, std::vector<void*>& allocs);
 void fc_tc_init();
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
-                  int64_t M, int N, int K, bool relu, cudaStream_t st);
+                  int64_t M, int N, int K, bool relu, cudaStream_t st, bool pack_img = false);
+uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs);
 // dispatch (api.cu)
 void forward(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
              float* logits, cudaStream_t st);

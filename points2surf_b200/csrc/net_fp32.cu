@@ -419,7 +419,7 @@ void feat(const Feat& f, const float* pts, int64_t Bc, int n, Ws& w, float* fmax
 void forward_fp32(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
                   float* logits, cudaStream_t st) {
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size, PS = P + S;
-    const int64_t Bc_max = 256;
+    const int64_t Bc_max = 1024;
     // carve the workspace
     size_t per_q = (size_t)PS * 3 * 3 + (size_t)PS * (64 + 128 + 128) + 1024 * 3 + 512 * 3 + 256 + 4 + 9 + 4096 + 1024 + 256 + 128 + 64;
     float* base = m.ws_net.as<float>(per_q * Bc_max);

@@ -517,6 +517,25 @@ __global__ void __launch_bounds__(256) fold_w1_kernel(const float* __restrict__ 
     }
 }
 
+// conv1 folded into the STN's last layer: W1*(T+I) with T = view(fc3(f) + b, 64, 64) is linear in f, so
+//   (W1*(T+I))[o][i] = sum_k f[k] * G[o*64+i][k] + g0[o*64+i],
+//   G[o*64+i][k] = sum_j W1[o][j] * Wfc3[j*64+i][k],   g0[o*64+i] = sum_j W1[o][j] * bfc3[j*64+i] + W1[o][i].
+// One FC layer then yields the per-query operand directly (model.py:62-68,196,201).
+__global__ void fold_fc3_kernel(const float* __restrict__ W1, const float* __restrict__ Wfc3, const float* __restrict__ bfc3,
+                                float* __restrict__ G, float* __restrict__ g0) {
+    const int oi = blockIdx.x;                 // o*64 + i
+    const int o = oi >> 6, i = oi & 63;
+    const int k = threadIdx.x;                 // 0..255 (fc3 input width)
+    float acc = 0.f;
+    for (int j = 0; j < 64; ++j) acc = fmaf(W1[o * 64 + j], Wfc3[(size_t)(j * 64 + i) * 256 + k], acc);
+    G[(size_t)oi * 256 + k] = acc;
+    if (k == 0) {
+        float b = W1[o * 64 + i];
+        for (int j = 0; j < 64; ++j) b = fmaf(W1[o * 64 + j], bfc3[j * 64 + i], b);
+        g0[oi] = b;
+    }
+}
+
 // out[b][i][j] = in[b][j][i] for 64x64 blocks (the STN's transform, transposed for the W1*T product)
 __global__ void transpose64_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -572,6 +591,9 @@ struct TcWeights {
     TcStack stn[2], fin[2];      // [0] local, [1] global: pass B, pass C
     TcStnFc qstn_fc, stn_fc[2];
     TcFc head_fc1[2], head_fc2, head_fc3;
+    // conv1 folded into stn2.fc3 per branch: images of G [4096 x 256] and bias g0 [4096]
+    const uint8_t* fold_img[2] = {nullptr, nullptr};
+    const float* fold_bias[2] = {nullptr, nullptr};
     bool fc_on_tc = true;
     std::vector<void*> allocs;
     int sm_count = 148;
@@ -711,6 +733,15 @@ void tc_build(Model& m) {
     else if (m.global.has_qstn) t->qstn_fc = mk_stn_fc(m.global.stn1);
     t->stn_fc[0] = mk_stn_fc(m.local.stn2);
     t->stn_fc[1] = mk_stn_fc(m.global.stn2);
+    for (int br = 0; br < 2; ++br) {
+        const Feat& f = br ? m.global : m.local;
+        P2S_CHECK(f.stn2.fc3.cout == 4096 && f.stn2.fc3.cin == 256 && f.conv1.cout == 64 && f.conv1.cin == 64, "unexpected STN shape");
+        float* G = reinterpret_cast<float*>(tc_alloc(*t, (size_t)4096 * 256 * 4));
+        float* g0 = reinterpret_cast<float*>(tc_alloc(*t, 4096 * 4));
+        P2S_LAUNCH(fold_fc3_kernel, 4096, 256, 0, 0, f.conv1.W, f.stn2.fc3.W, f.stn2.fc3.b, G, g0);
+        t->fold_img[br] = fc_tc_pack_raw(G, 4096, 256, t->allocs);
+        t->fold_bias[br] = g0;
+    }
     t->head_fc1[0] = mk_fc(m.fc1_local);
     t->head_fc1[1] = mk_fc(m.fc1_global);
     t->head_fc2 = mk_fc(m.fc2);
@@ -790,9 +821,19 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
             { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st); }
-            { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], t.fc_on_tc, gmax, Bc, g, f1, f2, T, st); }
-            // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
-            { StageScope ts("net: fold W1*T", st); P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq); }
+            if (t.fc_on_tc) {
+                // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
+                StageScope ts("net: fc tails", st);
+                P2S_CUDA(cudaMemcpyAsync(g, gmax, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
+                launch_bias_act(g, f.stn2.c3.b, Bc, 1024, true, st);
+                run_fc(t.stn_fc[br].fc1, g, 1024, f1, 512, Bc, true, true, st);
+                run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
+                launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, true);
+            } else {
+                { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], false, gmax, Bc, g, f1, f2, T, st); }
+                // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
+                { StageScope ts("net: fold W1*T", st); P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq); }
+            }
             (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
             { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st); }
