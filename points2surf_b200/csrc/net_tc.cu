@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t pack_relu(float a, float b) {
     return r;
 }
 
-__global__ void __maxnreg__(88) pointnet_pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [2][3][64]: rows of (W0*R)^T per chain
     float* s_bias = s_wq + 192;                                           // [256] mid biases back to back, [64] first-layer bias
