@@ -16,9 +16,9 @@
 // a per-thread reduction over TMEM columns (no shuffles).  Each CTA owns 512 of the 1024 channels (its half
 // of W3, 128 KB fp16, stays resident in shared memory); CTA 2j and 2j+1 stream the same queries.
 //
-// Warp roles (704 threads): warps 14-17 compute the first layer (fp32 FMA) of every tile; warps 0-3 and 9-12 are two
-// chains (even / odd tiles) running the mid-layer epilogues (thread = point = TMEM lane); warps 4-7 and 18-21 the
-// column-max epilogue of the big layer (each group takes half of the accumulator's columns); warp 8 issues the big-layer MMAs (blocking waits), warp 13 the mid-layer MMAs of both
+// Warp roles (576 threads): warps 14-17 compute the first layer (fp32 FMA) of every tile; warps 0-3 and 9-12 are two
+// chains (even / odd tiles) running the mid-layer epilogues (thread = point = TMEM lane); warps 4-7 the column-max
+// epilogue of the big layer; warp 8 issues the big-layer MMAs (blocking waits), warp 13 the mid-layer MMAs of both
 // chains (polling).
 //
 // The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
@@ -36,7 +36,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kThreads = 704;   // warps 0-3 chain 0 | 4-7 + 18-21 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer | 14-17 first layer
+constexpr int kThreads = 576;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer | 14-17 first layer
 // shared memory map (bytes)
 constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
 constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
@@ -51,7 +51,7 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM map (columns)
 constexpr uint32_t kColD3 = 0;      // 2 stages x 128
 constexpr uint32_t kColDmid = 256;  // 128 columns: accumulator of the 128-channel mid layers (shared by the chains)
-constexpr uint32_t kColScratch = 448; // 2 x 4 columns: partial maxima handed from epilogue warps 18-21 to warps 4-7
+constexpr uint32_t kColDmidB = 448; // 64 columns: accumulator of the 64-channel mid layers (shared by the chains)
 constexpr uint32_t kColA = 384;     // 2 chains x 32 (fp16 pairs, K = 64)
 
 struct Seg {
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             mbar_init(&bars->act2_full[i], 128);
             mbar_init(&bars->act2_empty[i], 1);
             mbar_init(&bars->d3_full[i], 1);
-            mbar_init(&bars->d3_empty[i], 256);
+            mbar_init(&bars->d3_empty[i], 128);
         }
         fence_mbar_init();
     }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             int it_mid0 = 0, it_mid1 = 1, l_mid0 = 0, l_mid1 = 0;
             uint32_t rnd0 = 0, rnd1 = 0;        // per-chain (tile, layer) round counter
             uint32_t g_mid = 0;                 // mid MMAs issued so far (alternates which chain is polled first)
-            uint32_t g_buf0 = 0;                // MMAs issued into the shared mid-layer accumulator
+            uint32_t g_buf0 = 0, g_buf1 = 0;    // MMAs issued into the 128-column / 64-column accumulator
             int loaded_q = 0, perq_count = 0;   // per-query weights resident for local query `loaded_q`
             bool pq_loading = false;
             while (it_mid0 < ntiles || it_mid1 < ntiles) {
@@ -244,13 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
                     if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
-                    uint32_t& g_buf = g_buf0;
-                    if (g_buf > 0) wait_bar(&bars->dmid_free[0], (g_buf - 1) & 1);   // short: the previous read-out
+                    const bool small = (p.mid_N[l] == 64);
+                    uint32_t& g_buf = small ? g_buf1 : g_buf0;
+                    if (g_buf > 0) wait_bar(&bars->dmid_free[small ? 1 : 0], (g_buf - 1) & 1);   // short: the previous read-out
                     tc_fence_after();
                     const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
                     const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
                     const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
-                    const uint32_t d_t = tmem + kColDmid;
+                    const uint32_t d_t = tmem + (small ? kColDmidB : kColDmid);
                     const bool pq_last = (l == p.perq_layer) && (perq_count + 1 == tpq);
                     if (elect_one()) {
 #pragma unroll
@@ -288,14 +289,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     tc_fence_before();              // the first-layer warps may write the next tile's operand
                     mbar_arrive(&bars->a_free[c]);
                 }
-                const uint32_t dcol = kColDmid;
+                const uint32_t dcol = (N == 64) ? kColDmidB : kColDmid;
                 for (int n0 = 0; n0 < N; n0 += 32) {
                     uint32_t r[32];
                     tmem_ld_x32(tmem + lane_base + dcol + n0, r);
                     tmem_ld_wait();
                     if (n0 + 32 >= N) {            // accumulator fully read: hand it to the other chain
                         tc_fence_before();
-                        mbar_arrive(&bars->dmid_free[0]);
+                        mbar_arrive(&bars->dmid_free[N == 64 ? 1 : 0]);
                     }
                     uint32_t v[16];
 #pragma unroll
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 boff += N;
             }
         }
-    } else if (warp >= 14 && warp < 18) {
+    } else if (warp >= 14) {
         // =============================================================== first layer (fp32 FMA) for both chains
         // thread = point = TMEM lane; produces the K = 64 fp16 A operand of the first mid layer of tile `it` in the
         // A columns of chain it & 1 as soon as that chain has released them.
@@ -412,12 +413,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         }
     } else {
         // =============================================================== big-layer epilogue: max over the tile's points
-        // two warpgroups split every accumulator by columns (points): warps 4-7 take columns 0-63, warps 18-21
-        // columns 64-127; at the end of a query the second group hands its partial maxima over through TMEM
-        const int eh = (warp >= 18) ? 1 : 0;
-        const int grp = warp & 3;
-        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
-        const int ch_lane = grp * 32 + lane;
+        const int ew = warp - 4;
+        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        const int ch_lane = ew * 32 + lane;
         int it = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int q = stream + qi * nstreams;
@@ -429,38 +427,28 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const uint32_t stage = g & 1, use = g >> 1;
                     wait_bar(&bars->d3_full[stage], use & 1);
                     tc_fence_after();
-                    const uint32_t d = tmem + lane_base + kColD3 + stage * 128u + (uint32_t)eh * 64u;
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_x32(d, r0);
-                    tmem_ld_x32(d + 32, r1);
-                    tmem_ld_wait();
-                    tc_fence_before();                  // this half is in registers: release the stage before reducing
-                    mbar_arrive(&bars->d3_empty[stage]);
+                    const uint32_t d = tmem + lane_base + kColD3 + stage * 128u;
                     float m = acc[c];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+                    for (int n0 = 0; n0 < 128; n0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld_x32(d + n0, r0);
+                        tmem_ld_x32(d + n0 + 32, r1);
+                        tmem_ld_wait();
+                        if (n0 == 64) {             // accumulator fully read: release the stage before reducing
+                            tc_fence_before();
+                            mbar_arrive(&bars->d3_empty[stage]);
+                        }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+                        for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+                    }
                     acc[c] = m;
                 }
             }
-            const uint32_t sc = tmem + lane_base + kColScratch + (uint32_t)(qi & 1) * 4u;
-            if (eh) {
-                uint32_t v[4] = {__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3])};
-                tmem_st_x4(sc, v);
-                tmem_st_wait();
-                tc_fence_before();
-                asm volatile("bar.sync 4, 256;" ::: "memory");
-            } else {
-                asm volatile("bar.sync 4, 256;" ::: "memory");
-                tc_fence_after();
-                uint32_t v[4];
-                tmem_ld_x4(sc, v);
-                tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    p.out[(size_t)q * 1024 + half * 512 + c * 128 + ch_lane] = fmaxf(acc[c], __uint_as_float(v[c]));
-            }
+            for (int c = 0; c < 4; ++c) p.out[(size_t)q * 1024 + half * 512 + c * 128 + ch_lane] = acc[c];
         }
     }
     tc_fence_before();
