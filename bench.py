@@ -264,8 +264,13 @@ def run_b200(args):
         if prof and prof['launches'] > 0:
             peak = peaks.get('bf16_tflops_sustained') or 1400.0
             ach = prof['flops'] / (prof['ms'] * 1e-3) / 1e12
+            traffic = None
+            try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel
+                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_pass_traffic.json')))['traffic_bytes_per_launch_mean']
+            except Exception:
+                pass
             roofline = {'bound': 'tensor', 'kernel': prof['kernel'], 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                        'frac': ach / peak, 'traffic': None,
+                        'frac': ach / peak, 'traffic': traffic,
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
                         'flops_per_launch': prof['flops'] / prof['launches'], 'ms_per_launch': prof['ms'] / prof['launches'],
                         'share_of_step': prof['ms'] / dev_ms}
