@@ -240,6 +240,32 @@ def run_b200(args):
     sampler.start()
     dev_ms, launches = timed(step_dev, args.steps, max(args.warmup, 3))
     guard_total = eng.last_guard_count() if precision == 'tc' else 0   # warm-up + timed steps
+
+    # second half of the metric ("shapes/sec reconstructed"): SDF band -> volume -> sign propagation -> marching cubes,
+    # measured on this rank's shape outside the queries/s region (HBM/L2-bound byte kernels)
+    mesh_stage = None
+    if rank == 0:
+        lin, sdf = step_dev()
+        res = args.grid_res
+        for _ in range(2):
+            vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
+            v, f = ops.marching_cubes(vol, 0.0)
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
+        e1.record()
+        v, f = ops.marching_cubes(vol, 0.0)
+        e2.record()
+        torch.cuda.synchronize()
+        t_vol, t_mc = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        vox = float(res) ** 3
+        mesh_stage = {'sign_propagation_ms': t_vol, 'sign_propagation_iterations': int(iters),
+                      'sign_propagation_GBps': (vox * 10.0 * max(iters, 1) + vox * 13.0) / (t_vol * 1e-3) / 1e9,
+                      'marching_cubes_ms': t_mc, 'verts': int(v.shape[0]), 'faces': int(f.shape[0]),
+                      'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + v.shape[0] * 12.0 + f.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
+                      'bytes_model': 'sign propagation: res^3 * (10 B per iteration + 13 B init/finalize); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
+                      'shapes_per_s_incl_mesh': 1e3 / (dev_ms / args.steps + t_vol + t_mc)}
     prof = eng.profile_get() if precision == 'tc' else None
     eng.profile_enable(False)
     sampler.stop_flag = True
@@ -291,6 +317,7 @@ def run_b200(args):
                              'sample': '%d queries evenly spaced over the band (assemble %.2fs, network %.2fs)'
                                        % (args.cpu_sample, cpu['t_assemble_s'], cpu['t_network_s'])},
             'tensor_flops_per_s': value * FLOP_PER_QUERY[args.model],
+            'mesh_stage': mesh_stage,
         }
         print(json.dumps(line))
     if world > 1:

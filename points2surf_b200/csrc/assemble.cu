@@ -131,81 +131,127 @@ __device__ __forceinline__ float norm_f32(float dx, float dy, float dz) {
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
+// One CTA walks kRun consecutive queries of the ordered list.  Consecutive voxel centres are close, so the exact
+// k-th distance of query j gives a *guaranteed* bound for query j+1 (triangle inequality:
+// kth(j+1) <= kth(j) + |q(j+1) - q(j)|): one pass collects every point within that bound (typically 1.1-1.2 k
+// candidates) and an exact sort finishes the job -- no histogram.  The first query of a run, big jumps between
+// queries and overflowing candidate lists fall back to the histogram selection.
+constexpr int kRun = 8;
+
 __global__ void __launch_bounds__(kThreads)
-knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int k,
+knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int64_t Q, int k,
                  int32_t* __restrict__ ids_out, float* __restrict__ patch_out, float* __restrict__ radius_out,
                  int* __restrict__ err_flag) {
     __shared__ SelectSmem s;
     __shared__ float red[kThreads / 32];
     __shared__ float s_radius;
+    __shared__ double s_kth;          // exact k-th squared distance of the previous query (0 = unknown)
     const int tid = threadIdx.x;
-    const int64_t q = blockIdx.x;
-    const float qxf = queries[q * 3 + 0], qyf = queries[q * 3 + 1], qzf = queries[q * 3 + 2];
-    const double qx = qxf, qy = qyf, qz = qzf;
-    auto keyfn = [&](int i) { return dkey(dist2_f64(pts, i, qx, qy, qz)); };
-
-    find_boundary(s, N, k, kCap - 512, keyfn);
-    if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
-    __syncthreads();
-    const int levels = s.levels;
-    // collect: keys below the boundary chain are members; keys inside it are candidates
-    for (int i = tid; i < N; i += kThreads) {
-        unsigned long long key = keyfn(i);
-        int c = chain_cmp(s, key, levels);
-        if (c < 0) {
-            // members go to the tail of the candidate arrays so one sort orders everything
-            unsigned slot = atomicAdd(&s.n_direct, 1u);
-            if (slot < (unsigned)kCap) { s.cand_key[kCap - 1 - slot] = key; s.cand_id[kCap - 1 - slot] = i; }
-        } else if (c == 0) {
-            unsigned slot = atomicAdd(&s.n_cand, 1u);
-            if (slot < (unsigned)kCap) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+    const int64_t q_begin = (int64_t)blockIdx.x * kRun;
+    const int64_t q_end = (q_begin + kRun < Q) ? (q_begin + kRun) : Q;
+    if (tid == 0) s_kth = 0.0;
+    double pqx = 0.0, pqy = 0.0, pqz = 0.0;
+    for (int64_t q = q_begin; q < q_end; ++q) {
+        __syncthreads();
+        const float qxf = queries[q * 3 + 0], qyf = queries[q * 3 + 1], qzf = queries[q * 3 + 2];
+        const double qx = qxf, qy = qyf, qz = qzf;
+        auto keyfn = [&](int i) { return dkey(dist2_f64(pts, i, qx, qy, qz)); };
+        // ---- fast path: bound from the previous query
+        bool done = false;
+        const double kth_prev = s_kth;
+        if (kth_prev > 0.0) {
+            const double ddx = qx - pqx, ddy = qy - pqy, ddz = qz - pqz;
+            const double delta = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+            const double rprev = sqrt(kth_prev);
+            if (delta < 0.25 * rprev) {
+                const double rb = (rprev + delta) * (1.0 + 1e-12);
+                const unsigned long long bound = dkey(rb * rb * (1.0 + 1e-12));
+                if (tid == 0) s.n_cand = 0;
+                __syncthreads();
+                for (int i = tid; i < N; i += kThreads) {
+                    unsigned long long key = keyfn(i);
+                    if (key <= bound) {
+                        unsigned slot = atomicAdd(&s.n_cand, 1u);
+                        if (slot < (unsigned)kCap) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+                    }
+                }
+                __syncthreads();
+                const unsigned n = s.n_cand;
+                if (n >= (unsigned)k && n <= (unsigned)kCap) {
+                    sort_candidates(s, (int)n);
+                    done = true;
+                }
+            }
         }
-    }
-    __syncthreads();
-    const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
-    if (n_direct + n_cand > (unsigned)kCap || n_direct != s.below) {
-        // more than kCap points tie into the boundary bin even after 3 refinement levels (degenerate cloud)
-        if (tid == 0) atomicExch(err_flag, 1);
-        return;
-    }
-    // compact: move the members right behind the candidates, then sort everything exactly
-    __syncthreads();
-    unsigned long long mk[(kCap + kThreads - 1) / kThreads];
-    int mi[(kCap + kThreads - 1) / kThreads];
-    int cnt = 0;
-    for (unsigned j = tid; j < n_direct; j += kThreads) { mk[cnt] = s.cand_key[kCap - 1 - j]; mi[cnt] = s.cand_id[kCap - 1 - j]; ++cnt; }
-    __syncthreads();
-    cnt = 0;
-    for (unsigned j = tid; j < n_direct; j += kThreads) { s.cand_key[n_cand + j] = mk[cnt]; s.cand_id[n_cand + j] = mi[cnt]; ++cnt; }
-    __syncthreads();
-    sort_candidates(s, (int)(n_direct + n_cand));
+        if (!done) {
+            // ---- histogram selection
+            __syncthreads();
+            find_boundary(s, N, k, kCap - 512, keyfn);
+            if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
+            __syncthreads();
+            const int levels = s.levels;
+            // collect: keys below the boundary chain are members; keys inside it are candidates
+            for (int i = tid; i < N; i += kThreads) {
+                unsigned long long key = keyfn(i);
+                int c = chain_cmp(s, key, levels);
+                if (c < 0) {
+                    // members go to the tail of the candidate arrays so one sort orders everything
+                    unsigned slot = atomicAdd(&s.n_direct, 1u);
+                    if (slot < (unsigned)kCap) { s.cand_key[kCap - 1 - slot] = key; s.cand_id[kCap - 1 - slot] = i; }
+                } else if (c == 0) {
+                    unsigned slot = atomicAdd(&s.n_cand, 1u);
+                    if (slot < (unsigned)kCap) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+                }
+            }
+            __syncthreads();
+            const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
+            if (n_direct + n_cand > (unsigned)kCap || n_direct != s.below) {
+                // more than kCap points tie into the boundary bin even after 3 refinement levels (degenerate cloud)
+                if (tid == 0) atomicExch(err_flag, 1);
+                return;
+            }
+            // compact: move the members right behind the candidates, then sort everything exactly
+            unsigned long long mk[(kCap + kThreads - 1) / kThreads];
+            int mi[(kCap + kThreads - 1) / kThreads];
+            int cnt = 0;
+            for (unsigned j = tid; j < n_direct; j += kThreads) { mk[cnt] = s.cand_key[kCap - 1 - j]; mi[cnt] = s.cand_id[kCap - 1 - j]; ++cnt; }
+            __syncthreads();
+            cnt = 0;
+            for (unsigned j = tid; j < n_direct; j += kThreads) { s.cand_key[n_cand + j] = mk[cnt]; s.cand_id[n_cand + j] = mi[cnt]; ++cnt; }
+            __syncthreads();
+            sort_candidates(s, (int)(n_direct + n_cand));
+        }
+        // exact k-th squared distance -> bound for the next query of the run
+        if (tid == 0) s_kth = __longlong_as_double((long long)s.cand_key[k - 1]);
+        pqx = qx; pqy = qy; pqz = qz;
 
-    // radius = max float32 norm over the k neighbours (utils.get_patch_radii)
-    float r = 0.f;
-    for (int j = tid; j < k; j += kThreads) {
-        int id = s.cand_id[j];
-        r = fmaxf(r, norm_f32(__fsub_rn(qxf, pts[id * 3 + 0]), __fsub_rn(qyf, pts[id * 3 + 1]), __fsub_rn(qzf, pts[id * 3 + 2])));
-    }
+        // radius = max float32 norm over the k neighbours (utils.get_patch_radii)
+        float r = 0.f;
+        for (int j = tid; j < k; j += kThreads) {
+            int id = s.cand_id[j];
+            r = fmaxf(r, norm_f32(__fsub_rn(qxf, pts[id * 3 + 0]), __fsub_rn(qyf, pts[id * 3 + 1]), __fsub_rn(qzf, pts[id * 3 + 2])));
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
-    if ((tid & 31) == 0) red[tid >> 5] = r;
-    __syncthreads();
-    if (tid == 0) {
-        float m = red[0];
-        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[w]);
-        s_radius = m;
-        radius_out[q] = m;
-    }
-    __syncthreads();
-    const float radius = s_radius;
-    for (int j = tid; j < k; j += kThreads) {
-        int id = s.cand_id[j];
-        if (ids_out) ids_out[q * k + j] = id;
-        float* o = patch_out + (q * k + j) * 3;
-        // model_space_to_patch_space: (p - q) / r in float32
-        o[0] = __fdiv_rn(__fsub_rn(pts[id * 3 + 0], qxf), radius);
-        o[1] = __fdiv_rn(__fsub_rn(pts[id * 3 + 1], qyf), radius);
-        o[2] = __fdiv_rn(__fsub_rn(pts[id * 3 + 2], qzf), radius);
+        for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if ((tid & 31) == 0) red[tid >> 5] = r;
+        __syncthreads();
+        if (tid == 0) {
+            float m = red[0];
+            for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[w]);
+            s_radius = m;
+            radius_out[q] = m;
+        }
+        __syncthreads();
+        const float radius = s_radius;
+        for (int j = tid; j < k; j += kThreads) {
+            int id = s.cand_id[j];
+            if (ids_out) ids_out[q * k + j] = id;
+            float* o = patch_out + (q * k + j) * 3;
+            // model_space_to_patch_space: (p - q) / r in float32
+            o[0] = __fdiv_rn(__fsub_rn(pts[id * 3 + 0], qxf), radius);
+            o[1] = __fdiv_rn(__fsub_rn(pts[id * 3 + 1], qyf), radius);
+            o[2] = __fdiv_rn(__fsub_rn(pts[id * 3 + 2], qzf), radius);
+        }
     }
 }
 
@@ -232,16 +278,21 @@ __global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, const 
     }
 }
 
-// CACHE: the per-point clock values live in dynamic shared memory (N floats) so that the distance, the Philox
-// block (shared by 4 consecutive points) and the logarithm are evaluated once per point instead of once per pass.
+// CACHE: per-point values live in dynamic shared memory (N floats) so that the distance, the Philox block (shared
+// by 4 consecutive points) and the logarithm are evaluated once per point.  With the cache the selection needs no
+// histogram: the clock of point i is Exp(1)/w_i, so the expected number of clocks below t is
+//   C(t) = sum_i (1 - exp(-w_i t)) = t*S1 - t^2*S2/2 + t^3*S3/6 - ...        (w_i t <~ 0.2 for S/N ~ 0.1)
+// Clocks <= t_lo (C = S - 5 sqrt(S)) are members, clocks in (t_lo, t_hi] (C = S + 5 sqrt(S)) are sorted exactly and
+// the smallest S - n_members of them complete the draw -- the same S smallest clocks as the histogram selection,
+// which takes over whenever the realised counts do not bracket S.
 template <bool CACHE>
 __global__ void __launch_bounds__(kThreads)
 subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries,
                           int64_t qbase, const int32_t* __restrict__ qidx, int S, uint64_t seed, int32_t* __restrict__ out, int* __restrict__ err_flag) {
-    extern __shared__ float s_key[];     // [N] when CACHE
+    extern __shared__ float s_val[];     // [N] when CACHE: distance, then weight
     __shared__ SelectSmem s;
-    __shared__ float red[kThreads / 32];
-    __shared__ float s_dmax;
+    __shared__ float red[3][kThreads / 32];
+    __shared__ float s_dmax, s_tlo, s_thi;
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
     const float qx = queries[q * 3 + 0], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
@@ -249,47 +300,101 @@ subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __r
     float dmax = 0.f;
     for (int i = tid; i < N; i += kThreads) {
         float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
-        if (CACHE) s_key[i] = d;
+        if (CACHE) s_val[i] = d;
         dmax = fmaxf(dmax, d);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    if ((tid & 31) == 0) red[tid >> 5] = dmax;
+    if ((tid & 31) == 0) red[0][tid >> 5] = dmax;
     __syncthreads();
     if (tid == 0) {
-        float m = red[0];
-        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[w]);
+        float m = red[0][0];
+        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, red[0][w]);
         s_dmax = m;
     }
     __syncthreads();
     dmax = s_dmax;
     const uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
-    // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
-    auto clock_of = [&](float d, uint32_t rnd) {
+    auto weight_of = [&](float d) {
         float dn = __fdiv_rn(d, dmax);
         float w = __fsub_rn(1.0f, __fmul_rn(1.5f, dn));
-        w = fminf(fmaxf(w, 0.05f), 1.0f);
-        return __fdividef(-__logf(u01_open(rnd)), w);
+        return fminf(fmaxf(w, 0.05f), 1.0f);
+    };
+    // exponential clock with rate w: the S earliest arrivals are a draw without replacement with p ~ w
+    auto clock_of = [&](float w, uint32_t rnd) { return __fdividef(-__logf(u01_open(rnd)), w); };
+    auto philox_block = [&](int i4, uint32_t (&r)[4]) {
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)i4, 0x77f1e2d3u, r);
     };
     if (CACHE) {
-        // one Philox block per 4 consecutive points
+        // ---- weights + their first three power sums
+        float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        for (int i = tid; i < N; i += kThreads) {
+            const float w = weight_of(s_val[i]);
+            s_val[i] = w;
+            m1 += w; m2 += w * w; m3 += w * w * w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+            m3 += __shfl_xor_sync(0xffffffffu, m3, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = m1; red[1][tid >> 5] = m2; red[2][tid >> 5] = m3; }
+        __syncthreads();
+        if (tid == 0) {
+            float S1 = 0.f, S2 = 0.f, S3 = 0.f;
+            for (int w = 0; w < kThreads / 32; ++w) { S1 += red[0][w]; S2 += red[1][w]; S3 += red[2][w]; }
+            auto solve = [&](float target) {
+                if (target <= 0.f) return 0.f;
+                float t = target / S1;
+                for (int it = 0; it < 6; ++it) {
+                    float f = t * (S1 - t * (0.5f * S2 - t * (S3 * (1.0f / 6.0f)))) - target;
+                    float fp = S1 - t * (S2 - 0.5f * t * S3);
+                    if (!(fp > 0.f)) break;
+                    t -= f / fp;
+                }
+                return t > 0.f ? t : 0.f;
+            };
+            const float sig = 5.0f * sqrtf((float)S);
+            s_tlo = solve((float)S - sig);
+            s_thi = solve((float)S + sig);
+            s.n_direct = 0; s.n_cand = 0;
+        }
+        __syncthreads();
+        const float tlo = s_tlo, thi = s_thi;
+        // ---- clocks (one Philox block per 4 consecutive points) and classification
         for (int i4 = tid; i4 * 4 < N; i4 += kThreads) {
             uint32_t r[4];
-            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)i4, 0x77f1e2d3u, r);
+            philox_block(i4, r);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int i = i4 * 4 + e;
-                if (i < N) s_key[i] = clock_of(s_key[i], r[e]);
+                if (i >= N) break;
+                const float c = clock_of(s_val[i], r[e]);
+                if (c <= tlo) {
+                    unsigned slot = atomicAdd(&s.n_direct, 1u);
+                    if (slot < (unsigned)S) out[q * S + slot] = i;
+                } else if (c <= thi) {
+                    unsigned slot = atomicAdd(&s.n_cand, 1u);
+                    if (slot < (unsigned)kCap) { s.cand_key[slot] = dkey((double)c); s.cand_id[slot] = i; }
+                }
             }
         }
         __syncthreads();
+        const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
+        if (n_direct <= (unsigned)S && n_direct + n_cand >= (unsigned)S && n_cand <= (unsigned)kCap) {
+            sort_candidates(s, (int)n_cand);
+            for (unsigned j = tid; n_direct + j < (unsigned)S; j += kThreads) out[q * S + n_direct + j] = s.cand_id[j];
+            return;
+        }
+        __syncthreads();     // counts did not bracket S: histogram selection below (cache holds the weights)
     }
     auto keyfn = [&](int i) {
-        if (CACHE) return dkey((double)s_key[i]);
-        float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
         uint32_t r[4];
-        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)(i >> 2), 0x77f1e2d3u, r);
-        return dkey((double)clock_of(d, r[i & 3]));
+        philox_block(i >> 2, r);
+        const float w = CACHE ? s_val[i]
+                              : weight_of(norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2])));
+        return dkey((double)clock_of(w, r[i & 3]));
     };
     find_boundary(s, N, S, kCap, keyfn);
     if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
@@ -351,7 +456,7 @@ void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int
     P2S_CHECK(k >= 1 && k <= 512, "k must be in [1, 512]");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
-    P2S_LAUNCH(knn_patch_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, k, ids, patch, radius, err_flag_dev());
+    P2S_LAUNCH(knn_patch_kernel, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
 }
 
 // the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q)
