@@ -249,21 +249,21 @@ def run_b200(args):
         res = args.grid_res
         for _ in range(2):
             vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
-            v, f = ops.marching_cubes(vol, 0.0)
+            mv, mf = ops.marching_cubes(vol, 0.0)
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
         e1.record()
-        v, f = ops.marching_cubes(vol, 0.0)
+        mv, mf = ops.marching_cubes(vol, 0.0)
         e2.record()
         torch.cuda.synchronize()
         t_vol, t_mc = e0.elapsed_time(e1), e1.elapsed_time(e2)
         vox = float(res) ** 3
         mesh_stage = {'sign_propagation_ms': t_vol, 'sign_propagation_iterations': int(iters),
                       'sign_propagation_GBps': (vox * 10.0 * max(iters, 1) + vox * 13.0) / (t_vol * 1e-3) / 1e9,
-                      'marching_cubes_ms': t_mc, 'verts': int(v.shape[0]), 'faces': int(f.shape[0]),
-                      'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + v.shape[0] * 12.0 + f.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
+                      'marching_cubes_ms': t_mc, 'verts': int(mv.shape[0]), 'faces': int(mf.shape[0]),
+                      'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + mv.shape[0] * 12.0 + mf.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
                       'bytes_model': 'sign propagation: res^3 * (10 B per iteration + 13 B init/finalize); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
                       'shapes_per_s_incl_mesh': 1e3 / (dev_ms / args.steps + t_vol + t_mc)}
     prof = eng.profile_get() if precision == 'tc' else None
