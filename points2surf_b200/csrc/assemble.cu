@@ -96,15 +96,17 @@ __device__ void find_boundary(SelectSmem& s, int N, int k, int cand_cap, KeyFn k
     }
 }
 
-// bitonic sort of (key, id) ascending over kCap slots (slots >= n are padded with +inf keys)
+// bitonic sort of (key, id) ascending over the first P = pow2ceil(n) slots (slots >= n are padded with +inf keys)
 __device__ void sort_candidates(SelectSmem& s, int n) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < kCap; i += kThreads)
+    int P = 64;
+    while (P < n) P <<= 1;                       // n <= kCap (checked by the callers), so P <= kCap
+    for (int i = tid; i < P; i += kThreads)
         if (i >= n) { s.cand_key[i] = ~0ull; s.cand_id[i] = 0x7fffffff; }
     __syncthreads();
-    for (int size = 2; size <= kCap; size <<= 1)
+    for (int size = 2; size <= P; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < kCap / 2; t += kThreads) {
+            for (int t = tid; t < P / 2; t += kThreads) {
                 int lo = 2 * t - (t & (stride - 1));
                 int hi = lo + stride;
                 bool up = ((lo & size) == 0);
@@ -168,7 +170,12 @@ knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__
                 const unsigned long long bound = dkey(rb * rb * (1.0 + 1e-12));
                 if (tid == 0) s.n_cand = 0;
                 __syncthreads();
+                // float32 pre-filter (relative error of the fp32 squared distance < 1e-6): only points that can be
+                // inside the bound pay for the exact float64 distance
+                const float bound_f = (float)(rb * rb) * 1.00001f;
                 for (int i = tid; i < N; i += kThreads) {
+                    const float fx = pts[i * 3 + 0] - qxf, fy = pts[i * 3 + 1] - qyf, fz = pts[i * 3 + 2] - qzf;
+                    if (fmaf(fx, fx, fmaf(fy, fy, fz * fz)) > bound_f) continue;
                     unsigned long long key = keyfn(i);
                     if (key <= bound) {
                         unsigned slot = atomicAdd(&s.n_cand, 1u);
