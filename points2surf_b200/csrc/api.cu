@@ -174,7 +174,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
                 const int64_t n = (ng - g0 < batch) ? (ng - g0) : batch;
                 gather_i32(lin_idx, glist + g0, n, glin, st);
                 assemble(glin, n, first_query, glist + g0);
-                forward_fp32(m, b.patch, b.sub, b.qpts, n, b.logits, st);
+                forward_guard(m, b.patch, b.sub, b.qpts, n, b.logits, st);
                 sdf_from_logits(b.logits, b.radius, n, gsdf, st);
                 scatter_f32(gsdf, glist + g0, n, sdf, st);
             }

@@ -96,16 +96,23 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             if (row < M && pack_img) {
                 // C is a per-row fp16 operand image of a [64][64] matrix (row-major index = column of this GEMM):
                 // K-major, LBO 128, SBO 1024 -- the per-query B operand of the pass kernel
-                uint8_t* img = reinterpret_cast<uint8_t*>(C) + (size_t)row * 8192;
+                // pack_img == 2: split precision, 16384 B per row: hi image | lo image
+                uint8_t* img = reinterpret_cast<uint8_t*>(C) + (size_t)row * (pack_img == 2 ? 16384 : 8192);
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     const int col = nt * 128 + n0 + j;
                     const int o = col >> 6, i = col & 63;
-                    uint32_t v[4];
+                    uint32_t v[4], vl[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        v[e] = pack_half2(__uint_as_float(r[j + 2 * e]) + b[n0 + j + 2 * e], __uint_as_float(r[j + 2 * e + 1]) + b[n0 + j + 2 * e + 1]);
-                    *reinterpret_cast<uint4*>(img + (uint32_t)(o >> 3) * 1024u + (uint32_t)(i >> 3) * 128u + (uint32_t)(o & 7) * 16u) = make_uint4(v[0], v[1], v[2], v[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const float x0 = __uint_as_float(r[j + 2 * e]) + b[n0 + j + 2 * e], x1 = __uint_as_float(r[j + 2 * e + 1]) + b[n0 + j + 2 * e + 1];
+                        v[e] = pack_half2(x0, x1);
+                        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&v[e]));
+                        vl[e] = pack_half2(x0 - hf.x, x1 - hf.y);
+                    }
+                    const uint32_t off = (uint32_t)(o >> 3) * 1024u + (uint32_t)(i >> 3) * 128u + (uint32_t)(o & 7) * 16u;
+                    *reinterpret_cast<uint4*>(img + off) = make_uint4(v[0], v[1], v[2], v[3]);
+                    if (pack_img == 2) *reinterpret_cast<uint4*>(img + 8192 + off) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
                 }
             } else if (row < M) {
 #pragma unroll
@@ -208,11 +215,11 @@ void fc_tc_init() {
 }
 
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
-                  int64_t M, int N, int K, bool relu, cudaStream_t st, bool pack_img) {
+                  int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img) {
     if (M <= 0) return;
     P2S_CHECK(fc_tc_supported(N, K) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
     dim3 grid((unsigned)cdiv(M, 128), (unsigned)(N / 128), 1);
-    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img ? 1 : 0);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img);
 }
 
 // images of a raw fp32 matrix W[N][K] (device pointer)

@@ -63,6 +63,7 @@ void tc_build(Model& m);
 void tc_destroy(Model& m);
 void tc_profile_reset(Model& m, bool on);
 void tc_profile_get(Model& m, double* ms, int64_t* launches, double* flops);
+void forward_guard(Model& m, const float* patch, const float* sub, const float* query, int64_t B, float* logits, cudaStream_t st);
 void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
                 float* logits, cudaStream_t st);
 // fc_tc.cu
@@ -70,7 +71,7 @@ bool fc_tc_supported(int N, int K);
 uint8_t* fc_tc_pack(const Layer& L, std::vector<void*>& allocs);
 void fc_tc_init();
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
-                  int64_t M, int N, int K, bool relu, cudaStream_t st, bool pack_img = false);
+                  int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img = 0);
 uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs);
 // dispatch (api.cu)
 void forward(Model& m, const float* patch, const float* sub, const float* query, int64_t B,

@@ -37,17 +37,27 @@ namespace {
 
 constexpr int kTile = 128;
 constexpr int kThreads = 576;   // warps 0-3 chain 0 | 4-7 column-max epilogue | 8 big-layer issuer | 9-12 chain 1 | 13 mid-layer issuer | 14-17 first layer
-// shared memory map (bytes)
-constexpr uint32_t kW3Bytes = 4 * 32768;                 // this CTA's 512 channels x 128 K, fp16
-constexpr uint32_t kMidBytes = 8192 + 8192 + 16384;      // 64x64, 64x64, 128x64 fp16
+// shared memory map (bytes).  PRECISE = split-precision variant used for the guard-band recompute: every fp16
+// operand x is carried as x_hi + x_lo and every product is evaluated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (three MMAs
+// per k-step, ~2^-22 relative), so the images are twice as large and a CTA owns one 128-channel chunk instead of four.
 constexpr uint32_t kAct2Bytes = 32768;                   // 128 points x 128 channels fp16
-constexpr uint32_t kOffW3 = 0;
-constexpr uint32_t kOffMid = kOffW3 + kW3Bytes;
-constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
-constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;
 constexpr uint32_t kSmallBytes = 192 * 4 + 320 * 4 + 168;  // Wq[3][64], biases[256 mid + 64 first], barriers
-constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+template <bool PRECISE>
+struct Cfg {
+    static constexpr int kChunks = PRECISE ? 1 : 4;                  // 128-channel chunks of the big layer per CTA
+    static constexpr int kSplit = 8 / kChunks;                       // CTAs that share one query stream
+    static constexpr uint32_t kChunkBytes = PRECISE ? 65536u : 32768u;   // W3 chunk image (hi [+ lo])
+    static constexpr uint32_t kW3Bytes = kChunks * kChunkBytes;
+    static constexpr uint32_t kMidBytes = (8192u + 8192u + 16384u) * (PRECISE ? 2u : 1u);
+    static constexpr uint32_t kOffMid = kW3Bytes;
+    static constexpr uint32_t kOffAct2 = kOffMid + kMidBytes;
+    static constexpr uint32_t kOffSmall = kOffAct2 + 2 * kAct2Bytes;   // normal: two tile buffers; precise: one buffer, hi | lo
+    static constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes;
+    static constexpr uint32_t kACols = PRECISE ? 64u : 32u;          // TMEM columns of one chain's A operand (hi [+ lo])
+    static constexpr uint32_t kPerqBytes = PRECISE ? 16384u : 8192u; // per-query conv1*(T+I) image
+    static constexpr uint32_t kMidScale = PRECISE ? 2u : 1u;
+};
+static_assert(Cfg<false>::kSmemBytes <= 232448 && Cfg<true>::kSmemBytes <= 232448, "shared memory budget");
 // TMEM map (columns)
 constexpr uint32_t kColD3 = 0;      // 2 stages x 128
 constexpr uint32_t kColDmid = 256;  // 128 columns: accumulator of the 128-channel mid layers (shared by the chains)
@@ -74,8 +84,8 @@ struct PassParams {
     const uint8_t* mid_img[3]; // packed fp16 operand images (K-major, LBO 128, SBO 1024)
     const float* mid_bias[3];
     int perq_layer;            // index of the mid layer with per-query weights, or -1
-    const uint8_t* perq_img;   // [B] x 8192 B
-    const uint8_t* w3_img;     // [2 halves][4 chunks][32768 B]  (K-major, LBO 128, SBO 2048)
+    const uint8_t* perq_img;   // [B] x 8192 B (precise: hi | lo, 16384 B)
+    const uint8_t* w3_img;     // [8 chunks][32768 B] (precise: [8][hi | lo])  (K-major, LBO 128, SBO 2048)
     float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer)
 };
 
@@ -108,15 +118,24 @@ __device__ __forceinline__ uint32_t pack_relu(float a, float b) {
     asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// split-precision variant: hi = fp16(relu(x)), lo = fp16(relu(x) - hi)
+__device__ __forceinline__ void pack_relu_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_relu(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_half2(fmaxf(a, 0.f) - hf.x, fmaxf(b, 0.f) - hf.y);
+}
 
+template <bool PRECISE>
 __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
+    using C = Cfg<PRECISE>;
+    constexpr uint32_t kOffMid = C::kOffMid, kOffAct2 = C::kOffAct2, kOffSmall = C::kOffSmall, kOffW3 = 0;
     extern __shared__ __align__(1024) uint8_t smem[];
-    float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [2][3][64]: rows of (W0*R)^T per chain
+    float* s_wq = reinterpret_cast<float*>(smem + kOffSmall);             // [3][64]: rows of (W0*R)^T
     float* s_bias = s_wq + 192;                                           // [256] mid biases back to back, [64] first-layer bias
     Bars* bars = reinterpret_cast<Bars*>(s_bias + 320);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int half = blockIdx.x & 1;
-    const int stream = blockIdx.x >> 1, nstreams = gridDim.x >> 1;
+    const int part = blockIdx.x % C::kSplit;                             // which 128-channel chunks this CTA owns
+    const int stream = blockIdx.x / C::kSplit, nstreams = gridDim.x / C::kSplit;
     const int nq = (p.B > stream) ? (p.B - stream + nstreams - 1) / nstreams : 0;   // queries of this CTA
     const int tpq = p.tiles_per_query;
     const int ntiles = nq * tpq;
@@ -157,19 +176,20 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         // The whole warp runs the warp-uniform loop; one elected lane issues the asynchronous instructions.
         if (ntiles > 0) {
             if (lane == 0) {
-                uint32_t bytes = kW3Bytes;
-                for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u;
+                uint32_t bytes = C::kW3Bytes;
+                for (int l = 0; l < p.num_mid; ++l) if (l != p.perq_layer) bytes += (uint32_t)p.mid_N[l] * 128u * C::kMidScale;
                 mbar_arrive_expect_tx(&bars->w_full, bytes);
-                for (int c = 0; c < 4; ++c)
-                    bulk_g2s(smem + kOffW3 + c * 32768, p.w3_img + ((size_t)half * 4 + c) * 32768, 32768, &bars->w_full);
+                for (uint32_t o = 0; o < C::kW3Bytes; o += 32768u)
+                    bulk_g2s(smem + kOffW3 + o, p.w3_img + (size_t)part * C::kW3Bytes + o, 32768, &bars->w_full);
                 uint32_t o = 0;
                 for (int l = 0; l < p.num_mid; ++l) {
-                    if (l != p.perq_layer) bulk_g2s(smem + kOffMid + o, p.mid_img[l], (uint32_t)p.mid_N[l] * 128u, &bars->w_full);
+                    const uint32_t lb = (uint32_t)p.mid_N[l] * 128u * C::kMidScale;
+                    if (l != p.perq_layer) bulk_g2s(smem + kOffMid + o, p.mid_img[l], lb, &bars->w_full);
                     else {
-                        mbar_arrive_expect_tx(&bars->wq_full, 8192);
-                        bulk_g2s(smem + kOffMid + o, p.perq_img + (size_t)stream * 8192, 8192, &bars->wq_full);
+                        mbar_arrive_expect_tx(&bars->wq_full, C::kPerqBytes);
+                        bulk_g2s(smem + kOffMid + o, p.perq_img + (size_t)stream * C::kPerqBytes, C::kPerqBytes, &bars->wq_full);
                     }
-                    o += (uint32_t)p.mid_N[l] * 128u;
+                    o += lb;
                 }
             }
             __syncwarp();
@@ -178,23 +198,34 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             const uint64_t dsc_w3 = make_smem_desc(smem_u32(smem + kOffW3), 128, 2048);
             const uint64_t dsc_act2 = make_smem_desc(smem_u32(smem + kOffAct2), 128, 2048);
             for (int it = 0; it < ntiles; ++it) {
-                const uint32_t buf = (uint32_t)it & 1;
-                wait_bar(&bars->act2_full[buf], ((uint32_t)it >> 1) & 1);
+                // normal: tile t uses activation buffer t & 1; precise: one buffer (hi | lo) used by every tile
+                const uint32_t buf = PRECISE ? 0u : ((uint32_t)it & 1), buse = PRECISE ? (uint32_t)it : ((uint32_t)it >> 1);
+                wait_bar(&bars->act2_full[buf], buse & 1);
                 const uint64_t db = dsc_act2 + (uint64_t)(buf * (kAct2Bytes >> 4));
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t g = (uint32_t)(it * 4 + c);
+                for (int c = 0; c < C::kChunks; ++c) {
+                    const uint32_t g = (uint32_t)(it * C::kChunks + c);
                     const uint32_t stage = g & 1, use = g >> 1;
                     wait_bar(&bars->d3_empty[stage], (use & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c * (32768u >> 4));
+                        const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c * (C::kChunkBytes >> 4));
                         const uint32_t d = tmem + kColD3 + stage * 128u;
+                        if (PRECISE) {
+                            const uint64_t da_lo = da + (uint64_t)(32768u >> 4), db_lo = db + (uint64_t)(32768u >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);
+                            for (int ks = 0; ks < 8; ++ks) {
+                                mma_ss(d, da_lo + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);   // small terms first
+                                mma_ss(d, da + (uint64_t)(ks * 16), db_lo + (uint64_t)(ks * 16), idesc_l3, 1);
+                                mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, 1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(d, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc_l3, ks > 0);
+                        }
                         mma_commit(&bars->d3_full[stage]);
-                        if (c == 3) mma_commit(&bars->act2_empty[buf]);
+                        if (c == C::kChunks - 1) mma_commit(&bars->act2_empty[buf]);
                     }
                     __syncwarp();
                 }
@@ -206,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             uint32_t mid_off[3] = {0, 0, 0};
             {
                 uint32_t o = 0;
-                for (int l = 0; l < p.num_mid; ++l) { mid_off[l] = o; o += (uint32_t)p.mid_N[l] * 128u; }
+                for (int l = 0; l < p.num_mid; ++l) { mid_off[l] = o; o += (uint32_t)p.mid_N[l] * 128u * C::kMidScale; }
             }
             const bool perq = p.perq_layer >= 0;
             wait_bar(&bars->w_full, 0);
@@ -228,9 +259,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 if (perq) {
                     if (!pq_loading && perq_count == tpq && loaded_q + 1 < nq && mbar_test_wait_warp(&bars->perq_done, (uint32_t)loaded_q & 1)) {
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(&bars->wq_full, 8192);
+                            mbar_arrive_expect_tx(&bars->wq_full, C::kPerqBytes);
                             bulk_g2s(smem + kOffMid + mid_off[p.perq_layer],
-                                     p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * 8192, 8192, &bars->wq_full);
+                                     p.perq_img + ((size_t)stream + (size_t)(loaded_q + 1) * nstreams) * C::kPerqBytes, C::kPerqBytes, &bars->wq_full);
                         }
                         __syncwarp();
                         pq_loading = true;
@@ -244,19 +275,29 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     const int l = l_m;
                     if (l == p.perq_layer && it_m / tpq != loaded_q) return;
                     if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
-                    const bool small = (p.mid_N[l] == 64);
+                    const bool small = !PRECISE && (p.mid_N[l] == 64);   // precise: the A operands occupy the small accumulator's columns
                     uint32_t& g_buf = small ? g_buf1 : g_buf0;
                     if (g_buf > 0) wait_bar(&bars->dmid_free[small ? 1 : 0], (g_buf - 1) & 1);   // short: the previous read-out
                     tc_fence_after();
                     const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
                     const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
-                    const uint32_t a_t = tmem + kColA + (uint32_t)c * 32u;
+                    const uint32_t a_t = tmem + kColA + (uint32_t)c * C::kACols;
                     const uint32_t d_t = tmem + (small ? kColDmidB : kColDmid);
                     const bool pq_last = (l == p.perq_layer) && (perq_count + 1 == tpq);
                     if (elect_one()) {
+                        if (PRECISE) {
+                            const uint64_t dsc_lo = dsc + (uint64_t)(((uint32_t)p.mid_N[l] * 128u) >> 4);   // lo image follows hi
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(d_t, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_ts(d_t, a_t + 32 + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);     // a_lo * b_hi
+                                mma_ts(d_t, a_t + ks * 8, dsc_lo + (uint64_t)(ks * 16), idesc, 1);          // a_hi * b_lo
+                                mma_ts(d_t, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, 1);             // a_hi * b_hi
+                            }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(d_t, a_t + ks * 8, dsc + (uint64_t)(ks * 16), idesc, ks > 0);
+                        }
                         mma_commit(&bars->dmid_ready[c]);
                         if (pq_last) mma_commit(&bars->perq_done);
                     }
@@ -275,9 +316,11 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         const int grp = warp & 3;                         // TMEM lane quarter this warp may access
         const int pt = grp * 32 + lane;                   // point (row) of the tile handled by this thread
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
-        const uint32_t a_col = tmem + lane_base + kColA + (uint32_t)c * 32u;
+        const uint32_t a_col = tmem + lane_base + kColA + (uint32_t)c * C::kACols;
         uint32_t round = 0;
         for (int it = c; it < ntiles; it += 2) {
+            const uint32_t ab = PRECISE ? 0u : (uint32_t)c;                              // activation buffer of this tile
+            const uint32_t au = PRECISE ? (uint32_t)it : ((uint32_t)it >> 1);           // its use count
             // ---- mid layers
             int boff = 0;
             for (int l = 0; l < p.num_mid; ++l, ++round) {
@@ -289,23 +332,29 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     tc_fence_before();              // the first-layer warps may write the next tile's operand
                     mbar_arrive(&bars->a_free[c]);
                 }
-                const uint32_t dcol = (N == 64) ? kColDmidB : kColDmid;
+                const bool small = !PRECISE && (N == 64);
+                const uint32_t dcol = small ? kColDmidB : kColDmid;
                 for (int n0 = 0; n0 < N; n0 += 32) {
                     uint32_t r[32];
                     tmem_ld_x32(tmem + lane_base + dcol + n0, r);
                     tmem_ld_wait();
                     if (n0 + 32 >= N) {            // accumulator fully read: hand it to the other chain
                         tc_fence_before();
-                        mbar_arrive(&bars->dmid_free[N == 64 ? 1 : 0]);
+                        mbar_arrive(&bars->dmid_free[small ? 1 : 0]);
                     }
-                    uint32_t v[16];
+                    uint32_t v[16], vl[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bb = *reinterpret_cast<const float4*>(s_bias + boff + n0 + 4 * j4);
                         const float2 s01 = fadd2(make_float2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), make_float2(bb.x, bb.y));
                         const float2 s23 = fadd2(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), make_float2(bb.z, bb.w));
-                        v[2 * j4] = pack_relu(s01.x, s01.y);
-                        v[2 * j4 + 1] = pack_relu(s23.x, s23.y);
+                        if (PRECISE) {
+                            pack_relu_split(s01.x, s01.y, v[2 * j4], vl[2 * j4]);
+                            pack_relu_split(s23.x, s23.y, v[2 * j4 + 1], vl[2 * j4 + 1]);
+                        } else {
+                            v[2 * j4] = pack_relu(s01.x, s01.y);
+                            v[2 * j4 + 1] = pack_relu(s23.x, s23.y);
+                        }
                     }
                     if (!last) {
                         // next layer's A operand (K index = channel, columns hold channel pairs); the MMA that read
@@ -316,24 +365,32 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
 #pragma unroll
                             for (int j = 0; j < 8; ++j) w[j] = v[h * 8 + j];
                             tmem_st_x8(a_col + (uint32_t)(n0 / 2 + h * 8), w);
+                            if (PRECISE) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) w[j] = vl[h * 8 + j];
+                                tmem_st_x8(a_col + 32u + (uint32_t)(n0 / 2 + h * 8), w);
+                            }
                         }
                     } else {
                         // big layer's B operand [point row][channel K] K-major, LBO 128, SBO 2048
-                        uint8_t* dst = smem + kOffAct2 + (uint32_t)c * kAct2Bytes + (uint32_t)(pt >> 3) * 2048u + (uint32_t)(pt & 7) * 16u;
+                        uint8_t* dst = smem + kOffAct2 + ab * kAct2Bytes + (uint32_t)(pt >> 3) * 2048u + (uint32_t)(pt & 7) * 16u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 4; ++j) {
                             *reinterpret_cast<uint4*>(dst + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (PRECISE)   // lo image of the single activation buffer
+                                *reinterpret_cast<uint4*>(dst + kAct2Bytes + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(vl[4 * j], vl[4 * j + 1], vl[4 * j + 2], vl[4 * j + 3]);
+                        }
                     }
                 }
                 if (!last) {
                     tmem_st_wait();
-                    if (l == p.num_mid - 2) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
+                    if (l == p.num_mid - 2) wait_bar(&bars->act2_empty[ab], (au & 1) ^ 1);
                     tc_fence_before();
                     mbar_arrive(&bars->a_ready[c]);
                 } else {
                     fence_proxy_async_smem();
                     tc_fence_before();
-                    mbar_arrive(&bars->act2_full[c]);
+                    mbar_arrive(&bars->act2_full[ab]);
                 }
                 boff += N;
             }
@@ -386,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 cur_q = qi;
             }
             x -= pcx; y -= pcy; z -= pcz;              // model.py:303
-            uint32_t v[32];
+            uint32_t v[32], vl[PRECISE ? 32 : 1];
 #pragma unroll
             for (int j4 = 0; j4 < 16; ++j4) {
                 const float4 wx = *reinterpret_cast<const float4*>(wq + 0 * 64 + 4 * j4);
@@ -397,17 +454,26 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 const float2 xx = make_float2(x, x), yy = make_float2(y, y), zz = make_float2(z, z);
                 const float2 h01 = ffma2(make_float2(wx.x, wx.y), xx, ffma2(make_float2(wy.x, wy.y), yy, ffma2(make_float2(wz.x, wz.y), zz, make_float2(bb.x, bb.y))));
                 const float2 h23 = ffma2(make_float2(wx.z, wx.w), xx, ffma2(make_float2(wy.z, wy.w), yy, ffma2(make_float2(wz.z, wz.w), zz, make_float2(bb.z, bb.w))));
-                v[2 * j4] = pack_relu(h01.x, h01.y);
-                v[2 * j4 + 1] = pack_relu(h23.x, h23.y);
+                if (PRECISE) {
+                    pack_relu_split(h01.x, h01.y, v[2 * j4], vl[2 * j4]);
+                    pack_relu_split(h23.x, h23.y, v[2 * j4 + 1], vl[2 * j4 + 1]);
+                } else {
+                    v[2 * j4] = pack_relu(h01.x, h01.y);
+                    v[2 * j4 + 1] = pack_relu(h23.x, h23.y);
+                }
             }
             if (it + 1 < ntiles) fetch(it + 1, x, y, z, pcx, pcy, pcz);     // next tile's point, in flight during the store
             wait_bar(&bars->a_free[c], (((uint32_t)it >> 1) & 1) ^ 1);
             tc_fence_after();
-            tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * 32u, v);
+            tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * C::kACols, v);
+            if (PRECISE) {
+                uint32_t (&vl32)[32] = reinterpret_cast<uint32_t (&)[32]>(vl);
+                tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * C::kACols + 32u, vl32);
+            }
             tmem_st_wait();
             // never trigger the last mid layer's MMA before this chain's act2 buffer is free: its epilogue must not
             // hold the shared D_mid accumulator while waiting for the big layer
-            if (p.num_mid == 1) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1);
+            if (p.num_mid == 1) wait_bar(&bars->act2_empty[PRECISE ? 0 : c], ((PRECISE ? (uint32_t)it : ((uint32_t)it >> 1)) & 1) ^ 1);
             tc_fence_before();
             mbar_arrive(&bars->a_ready[c]);
         }
@@ -419,11 +485,13 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         int it = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int q = stream + qi * nstreams;
-            float acc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float acc[C::kChunks];
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) acc[c] = -INFINITY;
             for (int tq = 0; tq < tpq; ++tq, ++it) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t g = (uint32_t)(it * 4 + c);
+                for (int c = 0; c < C::kChunks; ++c) {
+                    const uint32_t g = (uint32_t)(it * C::kChunks + c);
                     const uint32_t stage = g & 1, use = g >> 1;
                     wait_bar(&bars->d3_full[stage], use & 1);
                     tc_fence_after();
@@ -448,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) p.out[(size_t)q * 1024 + half * 512 + c * 128 + ch_lane] = acc[c];
+            for (int c = 0; c < C::kChunks; ++c) p.out[(size_t)q * 1024 + (part * C::kChunks + c) * 128 + ch_lane] = acc[c];
         }
     }
     tc_fence_before();
@@ -460,12 +528,15 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
 // weight packing (device side, once per model)
 // ------------------------------------------------------------------------------------------------
 // fp32 W[rows][K] -> fp16 K-major no-swizzle operand image: (r/8)*sbo + (k/8)*128 + (r%8)*16 + (k%8)*2
-__global__ void pack_kmajor_kernel(const float* __restrict__ W, int rows, int K, int row0, uint32_t sbo, uint8_t* __restrict__ img) {
+// lo = 1 writes the residual fp16(w - fp16(w)) instead (split-precision images)
+__global__ void pack_kmajor_kernel(const float* __restrict__ W, int rows, int K, int row0, uint32_t sbo, uint8_t* __restrict__ img, int lo) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= rows * K) return;
     int r = e / K, k = e % K;
     uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
-    *reinterpret_cast<__half*>(img + off) = __float2half_rn(W[(size_t)(row0 + r) * K + k]);
+    const float w = W[(size_t)(row0 + r) * K + k];
+    const __half h = __float2half_rn(w);
+    *reinterpret_cast<__half*>(img + off) = lo ? __float2half_rn(w - __half2float(h)) : h;
 }
 
 // per-query W1*T (fp32 [B][64][64], row = output channel) -> fp16 images of 8192 B
@@ -570,8 +641,10 @@ __global__ void guard_scatter_kernel(const float* __restrict__ src, const int32_
 
 // ------------------------------------------------------------------------------------------------
 struct TcStack {           // one conv stack ending in the 128 -> 1024 layer
-    uint8_t* w3_img = nullptr;     // 2 x 4 x 32768
+    uint8_t* w3_img = nullptr;     // 8 x 32768
     uint8_t* mid_img[3] = {nullptr, nullptr, nullptr};
+    uint8_t* w3_img_p = nullptr;   // split precision: 8 x (hi 32768 | lo 32768)
+    uint8_t* mid_img_p[3] = {nullptr, nullptr, nullptr};   // split precision: hi | lo
     const float* mid_bias[3] = {nullptr, nullptr, nullptr};
     int mid_N[3] = {0, 0, 0};
     int num_mid = 0;
@@ -617,22 +690,27 @@ uint8_t* tc_alloc(TcWeights& t, size_t bytes) {
     return (uint8_t*)p;
 }
 
-uint8_t* pack_layer(TcWeights& t, const Layer& L, uint32_t sbo) {   // whole layer as one image
-    uint8_t* img = tc_alloc(t, (size_t)L.cout * L.cin * 2);
-    P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, 0, sbo, img);
+uint8_t* pack_layer(TcWeights& t, const Layer& L, uint32_t sbo, bool split = false) {   // whole layer as one image (hi [| lo])
+    const size_t one = (size_t)L.cout * L.cin * 2;
+    uint8_t* img = tc_alloc(t, one * (split ? 2 : 1));
+    P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, 0, sbo, img, 0);
+    if (split) P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv((int64_t)L.cout * L.cin, 256), 256, 0, 0, L.W, L.cout, L.cin, 0, sbo, img + one, 1);
     return img;
 }
 
-uint8_t* pack_w3(TcWeights& t, const Layer& L) {   // 8 chunks of 128 rows, each its own 32 KB image
+uint8_t* pack_w3(TcWeights& t, const Layer& L, bool split = false) {   // 8 chunks of 128 rows, each its own image (hi [| lo])
     P2S_CHECK(L.cout == 1024 && L.cin == 128, "big layer must be 128 -> 1024");
-    uint8_t* img = tc_alloc(t, 8 * 32768);
-    for (int c = 0; c < 8; ++c)
-        P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv(128 * 128, 256), 256, 0, 0, L.W, 128, 128, c * 128, 2048u, img + (size_t)c * 32768);
+    const size_t chunk = split ? 65536 : 32768;
+    uint8_t* img = tc_alloc(t, 8 * chunk);
+    for (int c = 0; c < 8; ++c) {
+        P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv(128 * 128, 256), 256, 0, 0, L.W, 128, 128, c * 128, 2048u, img + (size_t)c * chunk, 0);
+        if (split) P2S_LAUNCH(pack_kmajor_kernel, (unsigned)cdiv(128 * 128, 256), 256, 0, 0, L.W, 128, 128, c * 128, 2048u, img + (size_t)c * chunk + 32768, 1);
+    }
     return img;
 }
 
 void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const float* query, const float* R,
-                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st) {
+                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st, bool precise) {
     PassParams p{};
     p.seg[0] = s0; p.seg[1] = s1;
     p.query = query; p.R = R;
@@ -640,21 +718,25 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
     p.B = (int)B;
     p.W0 = s.W0; p.b0 = s.b0;
     p.num_mid = s.num_mid;
-    for (int l = 0; l < 3; ++l) { p.mid_N[l] = s.mid_N[l]; p.mid_img[l] = s.mid_img[l]; p.mid_bias[l] = s.mid_bias[l]; }
+    for (int l = 0; l < 3; ++l) { p.mid_N[l] = s.mid_N[l]; p.mid_img[l] = precise ? s.mid_img_p[l] : s.mid_img[l]; p.mid_bias[l] = s.mid_bias[l]; }
     p.perq_layer = perq_layer;
     p.perq_img = perq_img;
-    p.w3_img = s.w3_img;
+    p.w3_img = precise ? s.w3_img_p : s.w3_img;
     p.out = out;
     TcWeights& t = *m.tc;
-    int grid = 2 * (t.sm_count / 2);
-    if ((int64_t)grid / 2 > B) grid = (int)(2 * B);
+    const int split = precise ? Cfg<true>::kSplit : Cfg<false>::kSplit;
+    int streams = t.sm_count / split;
+    if ((int64_t)streams > B) streams = (int)B;
+    const int grid = streams * split;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (t.prof_on) {
+    const bool prof = t.prof_on && !precise;
+    if (prof) {
         P2S_CUDA(cudaEventCreate(&e0)); P2S_CUDA(cudaEventCreate(&e1));
         P2S_CUDA(cudaEventRecord(e0, st));
     }
-    P2S_LAUNCH(pointnet_pass_kernel, grid, kThreads, kSmemBytes, st, p);
-    if (t.prof_on) {
+    if (precise) P2S_LAUNCH(pointnet_pass_kernel<true>, grid, kThreads, Cfg<true>::kSmemBytes, st, p);
+    else P2S_LAUNCH(pointnet_pass_kernel<false>, grid, kThreads, Cfg<false>::kSmemBytes, st, p);
+    if (prof) {
         P2S_CUDA(cudaEventRecord(e1, st));
         t.prof_events.emplace_back(e0, e1);
         // algorithmic FLOPs of this launch: real (un-padded) points, un-duplicated layers
@@ -691,20 +773,26 @@ void tc_build(Model& m) {
     cudaDeviceProp prop;
     P2S_CUDA(cudaGetDeviceProperties(&prop, m.device));
     t->sm_count = prop.multiProcessorCount;
-    P2S_CUDA(cudaFuncSetAttribute(pointnet_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    P2S_CUDA(cudaFuncSetAttribute(pointnet_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false>::kSmemBytes));
+    P2S_CUDA(cudaFuncSetAttribute(pointnet_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true>::kSmemBytes));
     auto build_stn = [&](TcStack& s, const Stn& stn, const Layer* c0a, const Layer* c0b) {
         // QSTN: x -> conv1(3->64) [layer 0] -> conv2 (64->128) -> conv3 ; STN64 on feat: conv0a [layer 0] -> conv0b -> conv1 -> conv2 -> conv3
         if (!c0a) {
             s.W0 = stn.c1.W; s.b0 = stn.c1.b;
             s.num_mid = 1;
             s.mid_img[0] = pack_layer(*t, stn.c2, 1024); s.mid_bias[0] = stn.c2.b; s.mid_N[0] = 128;
+            s.mid_img_p[0] = pack_layer(*t, stn.c2, 1024, true);
         } else {
             s.W0 = c0a->W; s.b0 = c0a->b;
             s.num_mid = 3;
             s.mid_img[0] = pack_layer(*t, *c0b, 1024); s.mid_bias[0] = c0b->b; s.mid_N[0] = 64;
             s.mid_img[1] = pack_layer(*t, stn.c1, 1024); s.mid_bias[1] = stn.c1.b; s.mid_N[1] = 64;
             s.mid_img[2] = pack_layer(*t, stn.c2, 1024); s.mid_bias[2] = stn.c2.b; s.mid_N[2] = 128;
+            s.mid_img_p[0] = pack_layer(*t, *c0b, 1024, true);
+            s.mid_img_p[1] = pack_layer(*t, stn.c1, 1024, true);
+            s.mid_img_p[2] = pack_layer(*t, stn.c2, 1024, true);
         }
+        s.w3_img_p = pack_w3(*t, stn.c3, true);
         s.w3_img = pack_w3(*t, stn.c3);
         s.b3 = stn.c3.b;
     };
@@ -714,6 +802,9 @@ void tc_build(Model& m) {
         s.mid_img[0] = pack_layer(*t, f.conv0b, 1024); s.mid_bias[0] = f.conv0b.b; s.mid_N[0] = 64;
         s.mid_img[1] = nullptr; s.mid_bias[1] = f.conv1.b; s.mid_N[1] = 64;       // per query: conv1 * T
         s.mid_img[2] = pack_layer(*t, f.conv2, 1024); s.mid_bias[2] = f.conv2.b; s.mid_N[2] = 128;
+        s.mid_img_p[0] = pack_layer(*t, f.conv0b, 1024, true);
+        s.mid_img_p[2] = pack_layer(*t, f.conv2, 1024, true);
+        s.w3_img_p = pack_w3(*t, f.conv3, true);
         s.w3_img = pack_w3(*t, f.conv3);
         s.b3 = f.conv3.b;
     };
@@ -782,20 +873,23 @@ void tc_profile_get(Model& m, double* ms, int64_t* launches, double* flops) {
     *flops = t.prof_flops;
 }
 
-void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
-                float* logits, cudaStream_t st) {
+// One pass of the network over B queries on tensor cores.  precise = split-precision operands everywhere
+// (the accurate path used for the guard band); fp16 operands otherwise.
+static void forward_tc_core(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+                            float* logits, cudaStream_t st, bool precise) {
     TcWeights& t = *m.tc;
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
     const int64_t Bc_max = 8192;
     // workspace (floats per query)
-    const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 2048 /* 8 KB perq image */ + 16;
+    const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 4096 /* 16 KB perq image (hi | lo) */ + 16;
     float* base = m.ws_net.as<float>(per_q * (size_t)Bc_max + 1024);
     float* pcur = base;
     auto take = [&](size_t n) { float* r = pcur; pcur += (n * (size_t)Bc_max + 63) / 64 * 64; return r; };
     float* gmax = take(1024); float* g = take(1024); float* f1 = take(512); float* f2 = take(256);
     float* q4 = take(4); float* R = take(9); float* T = take(4096); float* Tt = take(4096);
     float* fmax_l = take(1024); float* fmax_g = take(1024); float* cat = take(1024); float* h3 = take(256); float* h4 = take(128);
-    uint8_t* perq = reinterpret_cast<uint8_t*>(take(2048));
+    uint8_t* perq = reinterpret_cast<uint8_t*>(take(4096));
+    const bool fc_tc = t.fc_on_tc || precise;   // the precise path needs the split-precision FC kernel's image output
 
     for (int64_t b0 = 0; b0 < B; b0 += Bc_max) {
         const int64_t Bc = (B - b0 < Bc_max) ? (B - b0) : Bc_max;
@@ -805,13 +899,13 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
         const float* Rq = nullptr;
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st); }
-            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st, precise); }
+            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st); }
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
-            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st);
-            fc_tail(m.global.stn1.c3, t.qstn_fc, t.fc_on_tc, gmax, Bc, g, f1, f2, q4, st);
+            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st, precise);
+            fc_tail(m.global.stn1.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         }
@@ -820,15 +914,15 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st); }
-            if (t.fc_on_tc) {
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st, precise); }
+            if (fc_tc) {
                 // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
                 StageScope ts("net: fc tails", st);
                 P2S_CUDA(cudaMemcpyAsync(g, gmax, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
                 launch_bias_act(g, f.stn2.c3.b, Bc, 1024, true, st);
                 run_fc(t.stn_fc[br].fc1, g, 1024, f1, 512, Bc, true, true, st);
                 run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
-                launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, true);
+                launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
             } else {
                 { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], false, gmax, Bc, g, f1, f2, T, st); }
                 // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
@@ -836,17 +930,32 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             }
             (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st, precise); }
             launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
         StageScope ts_head("net: fc tails", st);
-        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, t.fc_on_tc, st);
-        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, t.fc_on_tc, st);
-        run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, t.fc_on_tc, st);
-        run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, t.fc_on_tc, st);
+        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, fc_tc, st);
+        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, fc_tc, st);
+        run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, fc_tc, st);
+        run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, fc_tc, st);
         launch_gemm_nt(h4, 0, 128, m.fc4.W, 0, m.fc4.b, logits + b0 * 2, 0, 2, (int)Bc, 2, 128, 1, false, st);
     }
+}
+
+// accurate recompute used for the guard band: split-precision tensor-core path (default) or the fp32 FMA path
+// (environment P2S_GUARD_FP32=1)
+void forward_guard(Model& m, const float* patch, const float* sub, const float* query, int64_t B, float* logits, cudaStream_t st) {
+    static int use_fp32 = -1;
+    if (use_fp32 < 0) { const char* e = getenv("P2S_GUARD_FP32"); use_fp32 = (e && e[0] == '1') ? 1 : 0; }
+    if (use_fp32) forward_fp32(m, patch, sub, query, B, logits, st);
+    else forward_tc_core(m, patch, sub, query, B, logits, st, true);
+}
+
+void forward_tc(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
+                float* logits, cudaStream_t st) {
+    const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
+    forward_tc_core(m, patch, sub, query, B, logits, st, false);
 
     // guard band: queries whose sign logit is too close to 0 for fp16-operand arithmetic are recomputed in fp32
     if (m.guard_band > 0.f && m.guard_list) {
@@ -869,7 +978,7 @@ void forward_tc(Model& m, const float* patch, const float* sub, const float* que
             P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * rowp, 256), 256, 0, st, patch, list, n, (int)rowp, gp);
             P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * rows, 256), 256, 0, st, sub, list, n, (int)rows, gs);
             P2S_LAUNCH(guard_gather_kernel, (unsigned)cdiv((int64_t)n * 3, 256), 256, 0, st, query, list, n, 3, gq);
-            forward_fp32(m, gp, gs, gq, n, gl, st);
+            forward_guard(m, gp, gs, gq, n, gl, st);
             P2S_LAUNCH(guard_scatter_kernel, (unsigned)cdiv(n, 256), 256, 0, st, gl, list, n, logits);
         }
     }

@@ -367,3 +367,26 @@ def test_subsample_weighted_large_cloud_uncached_path():
     assert all(len(set(r.tolist())) == 1000 for r in ids)
     d = np.linalg.norm(cloud[ids[0]] - cloud[0], axis=1)
     assert d.mean() < np.linalg.norm(cloud - cloud[0], axis=1).mean()      # near points are favoured
+
+
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_split_precision_tensor_core_path_matches_fp32(variant):
+    # a guard band wider than any logit sends every query through the accurate (hi/lo split, 3 MMAs per k-step)
+    # tensor-core path: it must agree with the fp32 FMA path to fp32 round-off, not to fp16 round-off
+    sd, inp, g = golden_model_case(variant)
+    args = (cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms']))
+    ref = make_engine(sd, variant, precision='fp32').forward(*args).cpu().numpy()
+    eng = make_engine(sd, variant, precision='tc', guard_band=1e9)
+    out = eng.forward(*args).cpu().numpy()
+    assert eng.last_guard_count() == 8
+    err = np.abs(out - ref).max()
+    print(variant, 'split-precision logit err vs fp32 path', err, 'vs oracle', np.abs(out - g['logits']).max())
+    assert err < 2e-3, err
+    assert np.abs(out - g['logits']).max() < 3e-3
+    # a larger ragged batch (several CTAs per stream, partial streams)
+    sd2 = calibrated_state_dict(variant, 21)
+    inp2 = synth.make_model_inputs(45, seed=9)
+    a2 = (cu(inp2['patch_pts_ps']), cu(inp2['pts_sub_sample_ms']), cu(inp2['imp_surf_query_point_ms']))
+    r2 = make_engine(sd2, variant, precision='fp32').forward(*a2).cpu().numpy()
+    o2 = make_engine(sd2, variant, precision='tc', guard_band=1e9).forward(*a2).cpu().numpy()
+    assert np.abs(o2 - r2).max() < 2e-3
