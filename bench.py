@@ -246,13 +246,14 @@ def run_b200(args):
     # second half of the metric ("shapes/sec reconstructed"): SDF band -> volume -> sign propagation -> marching cubes,
     # measured on this rank's shape outside the queries/s region (HBM/L2-bound byte kernels)
     mesh_stage = None
-    if rank == 0:
+    if True:
+        from points2surf_b200 import sharding
         lin, sdf = step_dev()
         res = args.grid_res
         for _ in range(2):
             vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
             mv, mf = ops.marching_cubes(vol, 0.0)
-        torch.cuda.synchronize()
+        barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
@@ -261,13 +262,27 @@ def run_b200(args):
         e2.record()
         torch.cuda.synchronize()
         t_vol, t_mc = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        # final mesh gather to rank 0 (NCCL over NVLink; the only data-path communication of the sharded run)
+        t_gather, gathered = 0.0, 1
+        if world > 1:
+            sharding.gather_meshes([(rank, mv, mf)], dst=0)   # warm-up (NCCL channel setup)
+            barrier()
+            t0 = time.perf_counter()
+            got = sharding.gather_meshes([(rank, mv, mf)], dst=0)
+            barrier()
+            t_gather = (time.perf_counter() - t0) * 1e3
+            gathered = len(got) if rank == 0 else 0
+        tt = torch.tensor([t_vol + t_mc, t_gather], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         vox = float(res) ** 3
         mesh_stage = {'sign_propagation_ms': t_vol, 'sign_propagation_iterations': int(iters),
                       'sign_propagation_GBps': (vox * 10.0 * max(iters, 1) + vox * 13.0) / (t_vol * 1e-3) / 1e9,
                       'marching_cubes_ms': t_mc, 'verts': int(mv.shape[0]), 'faces': int(mf.shape[0]),
                       'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + mv.shape[0] * 12.0 + mf.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
                       'bytes_model': 'sign propagation: res^3 * (10 B per iteration + 13 B init/finalize); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
-                      'shapes_per_s_incl_mesh': 1e3 / (dev_ms / args.steps + t_vol + t_mc)}
+                      'mesh_gather_ms': float(tt[1].item()), 'meshes_on_rank0': gathered,
+                      'shapes_per_s_incl_mesh': world * 1e3 / (dev_ms / args.steps + float(tt[0].item()) + float(tt[1].item()))}
     sampler.stop_flag = True
     sampler.join(timeout=2)
     e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
@@ -306,7 +321,7 @@ def run_b200(args):
             'metric': 'SDF queries/sec at grid_res=%d' % args.grid_res, 'value': value, 'unit': 'queries/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16 operands / f32 accumulate (tcgen05); f32 FC tails' if precision == 'tc' else 'f32',
+            'dtype': 'f16 operands / f32 accumulate (tcgen05); hi/lo split f16 (fp32-level) for FC tails and guard-band recompute' if precision == 'tc' else 'f32',
             'data': 'synthetic', 'config': dict(workload_config(args, Q), precision=precision, guard_band=guard,
                                                 guard_recompute_fraction=guard_frac),
             'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(cloud.nbytes), 'd2h_bytes_per_step': int(Q * 8)},

@@ -177,6 +177,25 @@ int p2s_marching_cubes_dev(const float* vol, int res, float level, float* verts,
                            int32_t* faces, int64_t fcap, int64_t* nverts_host, int64_t* nfaces_host,
                            void* stream);
 
+/* ------------------------------------------------------------------ mesh acceptance metric ----- */
+/* Area-weighted surface sampling (the sampler behind _chamfer_distance_single_file / _hausdorff_distance_single_file,
+ * source/base/evaluation.py:229-238; trimesh.sample.sample_surface without the "even" rejection step -- trimesh is
+ * absent, parity unpinned).  verts [V,3] fp32, faces [F,3] int32 -> samples [n,3] fp32, face_ids [n] int32 or NULL.
+ * Philox stream keyed by (seed, sample index).  async. */
+int p2s_mesh_sample_dev(const float* verts, int64_t V, const int32_t* faces, int64_t F, int64_t n,
+                        uint64_t seed, float* samples, int32_t* face_ids, void* stream);
+
+/* Exact nearest neighbour of every a[i] in b (cKDTree.query(a, 1), source/base/evaluation.py:246-250): dist [na]
+ * fp32 Euclidean distance, idx [na] int32 (lowest index on ties); either output may be NULL.  async. */
+int p2s_nn_distance_dev(const float* a, int64_t na, const float* b, int64_t nb, float* dist, int32_t* idx,
+                        void* stream);
+
+/* Both directed sums and maxima of the nearest-neighbour distances between two sample sets:
+ * out4_host = { sum a->b, sum b->a, max a->b, max b->a }.  Chamfer (evaluation.py:252-254) = out[0] + out[1];
+ * directed Hausdorff (evaluation.py:301-303) = out[2], out[3].  sync: result read-back. */
+int p2s_chamfer_hausdorff_dev(const float* a, int64_t na, const float* b, int64_t nb, double* out4_host,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

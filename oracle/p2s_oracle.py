@@ -399,3 +399,13 @@ def chamfer(new_samples, ref_samples):
     ref_new, _ = kd_new.query(ref_samples, 1)
     new_ref, _ = kd_ref.query(new_samples, 1)
     return float(np.sum(ref_new) + np.sum(new_ref))
+
+
+def hausdorff(new_samples, ref_samples):
+    """(directed new->ref, directed ref->new, symmetric) -- source/base/evaluation.py:301-304 (scipy's
+    directed_hausdorff is max-min of exact Euclidean distances; restated through cKDTree for speed)."""
+    import scipy.spatial as spatial
+    d_new_ref, _ = spatial.cKDTree(ref_samples).query(new_samples, 1)
+    d_ref_new, _ = spatial.cKDTree(new_samples).query(ref_samples, 1)
+    a, b = float(d_new_ref.max()), float(d_ref_new.max())
+    return a, b, max(a, b)

@@ -51,6 +51,9 @@ SIGNATURES = {
     'p2s_reconstruct_host': (C.c_int, [_vp, C.POINTER(ReconConfig), _vp, _i64, _vp, _vp, _i64, C.POINTER(_i64)]),
     'p2s_sdf_to_volume_dev': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, C.POINTER(C.c_int), _vp]),
     'p2s_marching_cubes_dev': (C.c_int, [_vp, _i32, _f32, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
+    'p2s_mesh_sample_dev': (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_uint64, _vp, _vp, _vp]),
+    'p2s_nn_distance_dev': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'p2s_chamfer_hausdorff_dev': (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(C.c_double), _vp]),
 }
 
 _lib = None

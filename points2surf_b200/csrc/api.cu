@@ -422,4 +422,27 @@ int p2s_marching_cubes_dev(const float* vol, int res, float level, float* verts,
     });
 }
 
+int p2s_mesh_sample_dev(const float* verts, int64_t V, const int32_t* faces, int64_t F, int64_t n, uint64_t seed,
+                        float* samples, int32_t* face_ids, void* stream) {
+    return guarded([&] {
+        P2S_CHECK(verts && faces && (samples || n == 0), "null argument");
+        mesh_sample(verts, V, faces, F, n, seed, samples, face_ids, as_stream(stream));
+    });
+}
+
+int p2s_nn_distance_dev(const float* a, int64_t na, const float* b, int64_t nb, float* dist, int32_t* idx,
+                        void* stream) {
+    return guarded([&] {
+        P2S_CHECK((a || na == 0) && b, "null argument");
+        nn_distance(a, na, b, nb, dist, idx, as_stream(stream));
+    });
+}
+
+int p2s_chamfer_hausdorff_dev(const float* a, int64_t na, const float* b, int64_t nb, double* out4_host, void* stream) {
+    return guarded([&] {
+        P2S_CHECK(a && b && out4_host, "null argument");
+        chamfer_hausdorff(a, na, b, nb, out4_host, as_stream(stream));
+    });
+}
+
 }  // extern "C"

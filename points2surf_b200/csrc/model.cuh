@@ -73,6 +73,11 @@ void fc_tc_init();
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
                   int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img = 0);
 uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs);
+// meshdist.cu
+void mesh_sample(const float* verts, int64_t V, const int32_t* faces, int64_t F, int64_t n, uint64_t seed,
+                 float* samples, int32_t* face_ids, cudaStream_t st);
+void nn_distance(const float* a, int64_t na, const float* b, int64_t nb, float* dist, int32_t* idx, cudaStream_t st);
+void chamfer_hausdorff(const float* a, int64_t na, const float* b, int64_t nb, double* out4_host, cudaStream_t st);
 // dispatch (api.cu)
 void forward(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
              float* logits, cudaStream_t st);

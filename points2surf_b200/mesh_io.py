@@ -116,3 +116,37 @@ def read_ply(file_path):
                     dt = np.dtype([(p[-1], '<' + tmap[p[0]]) for p in el['props']])
                     fp.read(dt.itemsize * el['count'])
     return verts, faces
+
+
+def read_off(file_path):
+    """OFF / COFF text files as written by write_off -> (vertices [V,3] float32, faces [F,3] int32)."""
+    with open(file_path) as fp:
+        tokens = fp.read().split()
+    head = tokens[0]
+    if head not in ('OFF', 'COFF'):
+        raise ValueError('not an OFF file: %s' % file_path)
+    nv, nf = int(tokens[1]), int(tokens[2])
+    per_v = (len(tokens) - 4 - 4 * nf) // max(nv, 1) if head == 'COFF' else 3   # xyz + colour components
+    pos = 4
+    vals = np.array(tokens[pos:pos + nv * per_v], dtype=np.float64).reshape(nv, per_v)
+    verts = vals[:, :3].astype(np.float32)
+    pos += nv * per_v
+    faces = np.zeros((nf, 3), np.int32)
+    for i in range(nf):
+        n = int(tokens[pos])
+        if n != 3:
+            raise ValueError('non-triangular face in %s' % file_path)
+        faces[i] = [int(t) for t in tokens[pos + 1:pos + 4]]
+        pos += 1 + n
+        # optional per-face colours are not written by write_off for triangle meshes
+    return verts, faces
+
+
+def read_mesh(file_path):
+    """Dispatch on the extension (.ply / .off) -> (vertices, faces)."""
+    ext = os.path.splitext(file_path)[1].lower()
+    if ext == '.ply':
+        return read_ply(file_path)
+    if ext == '.off':
+        return read_off(file_path)
+    raise ValueError('unsupported mesh format: %s' % file_path)

@@ -240,3 +240,39 @@ def marching_cubes(vol, level=0.0):
         check(lib.p2s_marching_cubes_dev(_ptr(vol), res, float(level), _ptr(verts), nv.value, _ptr(faces), nf.value,
                                          C.byref(nv), C.byref(nf), _stream()))
     return verts[:nv.value], faces[:nf.value]
+
+
+def mesh_sample(verts, faces, num_samples, seed=0, return_face_ids=False):
+    """Area-weighted surface samples [n,3] fp32 (the sampler of source/base/evaluation.py:229-238)."""
+    verts = _dev(verts, torch.float32, 'verts')
+    faces = _dev(faces, torch.int32, 'faces')
+    n = int(num_samples)
+    out = torch.empty((n, 3), dtype=torch.float32, device=verts.device)
+    fid = torch.empty((n,), dtype=torch.int32, device=verts.device) if return_face_ids else None
+    with torch.cuda.device(verts.device):
+        check(_lib.load().p2s_mesh_sample_dev(_ptr(verts), verts.shape[0], _ptr(faces), faces.shape[0], n,
+                                              int(seed) & (2**64 - 1), _ptr(out), _ptr(fid) if fid is not None else None,
+                                              _stream()))
+    return (out, fid) if return_face_ids else out
+
+
+def nn_distance(a, b):
+    """Nearest neighbour in b of every point of a -> (dist [na] fp32, idx [na] int32)  (cKDTree.query(a, 1))."""
+    a = _dev(a, torch.float32, 'a')
+    b = _dev(b, torch.float32, 'b')
+    dist = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    idx = torch.empty((a.shape[0],), dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.load().p2s_nn_distance_dev(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(dist), _ptr(idx), _stream()))
+    return dist, idx
+
+
+def chamfer_hausdorff(a, b):
+    """-> dict(chamfer, hausdorff_ab, hausdorff_ba, hausdorff) between two sample sets, the reference's definitions
+    (source/base/evaluation.py:252-254, 301-304)."""
+    a = _dev(a, torch.float32, 'a')
+    b = _dev(b, torch.float32, 'b')
+    out = (C.c_double * 4)()
+    with torch.cuda.device(a.device):
+        check(_lib.load().p2s_chamfer_hausdorff_dev(_ptr(a), a.shape[0], _ptr(b), b.shape[0], out, _stream()))
+    return {'chamfer': out[0] + out[1], 'hausdorff_ab': out[2], 'hausdorff_ba': out[3], 'hausdorff': max(out[2], out[3])}

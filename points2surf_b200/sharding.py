@@ -42,3 +42,50 @@ def gather_band(sdf_slab, counts, device=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[:c] for o, c in zip(out, counts)])
+
+
+def gather_meshes(meshes, dst=0):
+    """The "final mesh gather" of the shape-sharded run: every rank holds the meshes of its own
+    shapes as a list of (shape_index, verts [V,3] fp32, faces [F,3] int32) tensors on its device; rank `dst` receives
+    all of them, ordered by shape index, other ranks receive [].  One all_gather of the per-rank size table, then one
+    padded all_gather per buffer kind (NCCL over NVLink on GPUs, gloo on CPU) -- meshes are O(res^2) small, so a single
+    padded exchange beats per-mesh point-to-point sends."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return sorted(meshes, key=lambda m: m[0])
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = meshes[0][1].device if meshes else (torch.device('cuda', torch.cuda.current_device())
+                                              if dist.get_backend() == 'nccl' else torch.device('cpu'))
+    # size table: [n_meshes, then (shape_index, V, F) per mesh], padded to the largest mesh count
+    n_local = torch.tensor([len(meshes)], dtype=torch.int64, device=dev)
+    n_all = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(n_all, n_local)
+    n_max = max(int(n.item()) for n in n_all)
+    table = torch.zeros((max(n_max, 1), 3), dtype=torch.int64, device=dev)
+    for i, (idx, v, f) in enumerate(meshes):
+        table[i] = torch.tensor([idx, v.shape[0], f.shape[0]], dtype=torch.int64)
+    tables = [torch.zeros_like(table) for _ in range(world)]
+    dist.all_gather(tables, table)
+    tot_v = [int(t[:int(n.item()), 1].sum()) for t, n in zip(tables, n_all)]
+    tot_f = [int(t[:int(n.item()), 2].sum()) for t, n in zip(tables, n_all)]
+    vbuf = torch.zeros((max(max(tot_v), 1), 3), dtype=torch.float32, device=dev)
+    fbuf = torch.zeros((max(max(tot_f), 1), 3), dtype=torch.int32, device=dev)
+    if meshes:
+        vcat = torch.cat([m[1].reshape(-1, 3).to(torch.float32) for m in meshes])
+        fcat = torch.cat([m[2].reshape(-1, 3).to(torch.int32) for m in meshes])
+        vbuf[:vcat.shape[0]] = vcat
+        fbuf[:fcat.shape[0]] = fcat
+    vall = [torch.empty_like(vbuf) for _ in range(world)]
+    fall = [torch.empty_like(fbuf) for _ in range(world)]
+    dist.all_gather(vall, vbuf)
+    dist.all_gather(fall, fbuf)
+    if rank != dst:
+        return []
+    out = []
+    for r in range(world):
+        vo = fo = 0
+        for i in range(int(n_all[r].item())):
+            idx, nv, nf = (int(x) for x in tables[r][i])
+            out.append((idx, vall[r][vo:vo + nv].clone(), fall[r][fo:fo + nf].clone()))
+            vo += nv
+            fo += nf
+    return sorted(out, key=lambda m: m[0])

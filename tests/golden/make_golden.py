@@ -185,8 +185,42 @@ def gen_grid():
     np.savez_compressed(os.path.join(HERE, 'grid.npz'), **out)
 
 
+def gen_evaluation():
+    """eval_predictions / compare_predictions_binary_tensors / print_list_of_dicts of source/base/evaluation.py
+    (imports unmodified) on seeded inputs; the report text is the fixture."""
+    import contextlib
+    import io
+    from source.base import evaluation as ref_eval
+    rng = np.random.RandomState(11)
+    names = ['aa_b', 'cc', 'shape_with_long_name']
+    pred = {n: (rng.randn(2000) * (rng.rand(2000) > 0.1)).astype(np.float32) for n in names}
+    gt = {n: rng.randn(2000).astype(np.float32) for n in names}
+    out = {'names': np.array(names)}
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(d + '/pred'); os.makedirs(d + '/gt')
+        for n in names:
+            np.save(d + '/pred/' + n + '.xyz.npy', pred[n]); np.save(d + '/gt/' + n + '.ply.npy', gt[n])
+            out['pred_' + n] = pred[n]; out['gt_' + n] = gt[n]
+        for uns in (0, 1):
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref_eval.eval_predictions(d + '/pred', d + '/gt', d + '/rep.csv', unsigned=bool(uns))
+            out['report_unsigned%d' % uns] = np.array(open(d + '/rep.csv').read())
+    a, b = torch.from_numpy(rng.randn(64, 3)), torch.from_numpy(rng.randn(64, 3))
+    res = ref_eval.compare_predictions_binary_tensors(a, b, 'cmp')
+    out['bin_a'], out['bin_b'] = a.numpy(), b.numpy()
+    keys = sorted(k for k in res if k != 'comp_name')
+    out['bin_keys'] = np.array(keys); out['bin_vals'] = np.array([res[k] for k in keys], dtype=np.float64)
+    rows = [{'file': 'abc_def_ghi_jkl', 'mse': 1.23456789, 'x': 2.0}, {'file': 'zz', 'mse': 0.5, 'x': -1.0}]
+    for mode in ('latex', 'csv'):
+        with contextlib.redirect_stdout(io.StringIO()):
+            out['table_' + mode] = np.array('\n'.join(ref_eval.print_list_of_dicts(rows, None, mode)))
+    np.savez_compressed(os.path.join(HERE, 'evaluation.npz'), **out)
+    print('evaluation.npz written')
+
+
 if __name__ == '__main__':
     gen_grid()
+    gen_evaluation()
     gen_volume()
     gen_assembly()
     gen_model()

@@ -30,7 +30,18 @@ def _worker(rank, world, port, q):
         counts = [sharding.query_slab(Q, r, world)[1] for r in range(world)]
         band = sharding.gather_band(slab, counts)
         ms, units = sharding.reduce_timing(10.0 + rank, count)
-        q.put((rank, sharding.shapes_for_rank(7, rank, world), first, count, bool(torch.equal(band, full)), ms, units))
+        # final mesh gather: rank r owns shapes r, r+2, ... of 5; mesh i has i+1 vertices and 2i faces (shape 0: no faces)
+        mine = [(i, torch.full((i + 1, 3), float(i)), torch.full((2 * i, 3), i, dtype=torch.int32))
+                for i in sharding.shapes_for_rank(5, rank, world)]
+        got = sharding.gather_meshes(mine, dst=0)
+        if rank == 0:
+            mesh_ok = [g[0] for g in got] == list(range(5)) and all(
+                g[1].shape == (i + 1, 3) and g[2].shape == (2 * i, 3) and bool((g[1] == i).all()) and bool((g[2] == i).all())
+                for i, g in enumerate(got))
+        else:
+            mesh_ok = got == []
+        q.put((rank, sharding.shapes_for_rank(7, rank, world), first, count,
+               bool(torch.equal(band, full)) and mesh_ok, ms, units))
     finally:
         dist.destroy_process_group()
 
