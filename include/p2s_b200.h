@@ -196,6 +196,56 @@ int p2s_nn_distance_dev(const float* a, int64_t na, const float* b, int64_t nb, 
 int p2s_chamfer_hausdorff_dev(const float* a, int64_t na, const float* b, int64_t nb, double* out4_host,
                               void* stream);
 
+/* ------------------------------------------------------------------ training-step primitives --- */
+/* Row a14: loss + backward + SGD of source/points_to_surf_train.py:441-461,537-563 with the
+ * train-mode BatchNorm of source/points_to_surf_model.py.  Activations are row-major [rows, C] fp32.  The host side
+ * (points2surf_b200/train.py) sequences these like the reference's autograd graph.  All async on `stream`. */
+/* C[z][m][n] = act(sum_k A[z][m][k] W[z][n][k] + bias[n])   (torch conv1d(k=1) / linear / bmm forward) */
+int p2s_op_gemm_nt(const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z,
+                   const float* bias, float* C, int64_t c_stride_z, int ldc, int M, int N, int K, int batch,
+                   int relu, void* stream);
+/* C[z][n][k] (+)= sum_m A[z][m][n] B[z][m][k]               (weight gradient dW = dZ^T X) */
+int p2s_op_gemm_tn(const float* A, int64_t a_stride_z, int lda, const float* B, int64_t b_stride_z, int ldb,
+                   float* C, int64_t c_stride_z, int ldc, int M, int N, int K, int batch, int accumulate,
+                   void* stream);
+/* out[z][c][r] = in[z][r][c] */
+int p2s_op_transpose(const float* in, float* out, int rows, int cols, int batch, void* stream);
+/* BatchNorm1d(train): s1 = sum x, s2 = sum x^2 over the M rows (f64 [C] each) */
+int p2s_op_col_stats(const float* x, int64_t M, int C, double* s1, double* s2, void* stream);
+int p2s_op_col_sum(const float* x, int64_t M, int C, double* s1, void* stream);
+/* mean, invstd = 1/sqrt(biased var + eps); running stats updated like torch (unbiased var) when non-NULL */
+int p2s_op_bn_finalize(const double* s1, const double* s2, int64_t M, int C, float eps, float momentum,
+                       float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
+/* y = act(gamma (z - mean) invstd + beta) */
+int p2s_op_bn_apply(const float* z, int64_t M, int C, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, int relu, float* y, void* stream);
+/* dz from dy through act + BatchNorm(train); y = forward output for the ReLU mask or NULL; outputs s1 = dbeta,
+ * s2 = dgamma (f64 [C]) */
+int p2s_op_bn_backward(const float* dy, const float* z, const float* y, int64_t M, int C, const float* mean,
+                       const float* invstd, const float* gamma, double* s1, double* s2, float* dz, void* stream);
+/* MaxPool1d over the npts points of each query: y [B, npts, C] -> out [B, C], arg [B, C] (first maximum) */
+int p2s_op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, void* stream);
+int p2s_op_maxpool_bwd(const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, void* stream);
+/* compute_loss for outputs (imp_surf_magnitude, imp_surf_sign), source/points_to_surf_train.py:550-561 and
+ * source/sdf_nn.py:30-40: loss_out (device f64 [2]) = {w_mag * mse(tanh|p0|, tanh|t/r|), w_sign * bce(p1, s)};
+ * dpred [B,2] = gradient of their sum (NULL: forward only).  fixed_radius != 0 skips the division by r. */
+int p2s_op_loss(const float* pred, const float* target_mag, const float* radius, const float* target_sign,
+                int64_t B, float w_mag, float w_sign, int fixed_radius, double* loss_out, float* dpred,
+                void* stream);
+/* utils.batch_quat_to_rotmat (source/base/utils.py:13-46) forward and backward.  q4 [B,4] is the raw fc3 output of the
+ * QSTN; the identity quaternion (1,0,0,0) is added inside (source/points_to_surf_model.py:124-126).  R, dR [B,9]. */
+int p2s_op_quat_to_rot(const float* q4, float* R, int64_t B, void* stream);
+int p2s_op_quat_to_rot_bwd(const float* q4, const float* dR, int64_t B, float* dq, void* stream);
+/* x[b][:] += v[:]  (identity quaternion / identity matrix offsets) */
+int p2s_op_add_row(float* x, const float* v, int64_t B, int C, void* stream);
+/* out[b][p][:] = in[b][p][:] - q[b][:]  (source/points_to_surf_model.py:303) */
+int p2s_op_center(const float* in, const float* q, int64_t B, int npts, float* out, void* stream);
+/* y += a x */
+int p2s_op_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+/* torch.optim.SGD(momentum) update (source/points_to_surf_train.py:406,461) */
+int p2s_op_sgd(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+               int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,23 @@ SIGNATURES = {
     'p2s_marching_cubes_dev': (C.c_int, [_vp, _i32, _f32, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     'p2s_mesh_sample_dev': (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_uint64, _vp, _vp, _vp]),
     'p2s_nn_distance_dev': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'p2s_op_gemm_nt': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'p2s_op_gemm_tn': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'p2s_op_transpose': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    'p2s_op_col_stats': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    'p2s_op_col_sum': (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    'p2s_op_bn_finalize': (C.c_int, [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    'p2s_op_bn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    'p2s_op_bn_backward': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'p2s_op_maxpool_fwd': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    'p2s_op_maxpool_bwd': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    'p2s_op_loss': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp]),
+    'p2s_op_quat_to_rot': (C.c_int, [_vp, _vp, _i64, _vp]),
+    'p2s_op_quat_to_rot_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'p2s_op_add_row': (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    'p2s_op_center': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    'p2s_op_axpy': (C.c_int, [_vp, _vp, _f32, _i64, _vp]),
+    'p2s_op_sgd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _i32, _vp]),
     'p2s_chamfer_hausdorff_dev': (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(C.c_double), _vp]),
 }
 

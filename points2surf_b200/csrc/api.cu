@@ -445,4 +445,58 @@ int p2s_chamfer_hausdorff_dev(const float* a, int64_t na, const float* b, int64_
     });
 }
 
+// ---- training-step primitives (train_ops.cu)
+#define P2S_OP(name, params, ...)                                   \
+    int name params { return guarded([&] { __VA_ARGS__; }); }
+
+P2S_OP(p2s_op_gemm_nt, (const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z, const float* bias,
+                        float* C, int64_t c_stride_z, int ldc, int M, int N, int K, int batch, int relu, void* stream),
+       P2S_CHECK(A && W && C, "null argument");
+        launch_gemm_nt(A, a_stride_z, lda, W, w_stride_z, bias, C, c_stride_z, ldc, M, N, K, batch, relu != 0, as_stream(stream)))
+P2S_OP(p2s_op_gemm_tn, (const float* A, int64_t a_stride_z, int lda, const float* B, int64_t b_stride_z, int ldb, float* C,
+                        int64_t c_stride_z, int ldc, int M, int N, int K, int batch, int accumulate, void* stream),
+       P2S_CHECK(A && B && C, "null argument");
+        op_gemm_tn(A, a_stride_z, lda, B, b_stride_z, ldb, C, c_stride_z, ldc, M, N, K, batch, accumulate != 0, as_stream(stream)))
+P2S_OP(p2s_op_transpose, (const float* in, float* out, int rows, int cols, int batch, void* stream),
+       P2S_CHECK(in && out, "null argument"); op_transpose(in, out, rows, cols, batch, as_stream(stream)))
+P2S_OP(p2s_op_col_stats, (const float* x, int64_t M, int C, double* s1, double* s2, void* stream),
+       P2S_CHECK(x && s1 && s2, "null argument"); op_col_stats(x, M, C, s1, s2, as_stream(stream)))
+P2S_OP(p2s_op_col_sum, (const float* x, int64_t M, int C, double* s1, void* stream),
+       P2S_CHECK(x && s1, "null argument"); op_col_sum(x, M, C, s1, as_stream(stream)))
+P2S_OP(p2s_op_bn_finalize, (const double* s1, const double* s2, int64_t M, int C, float eps, float momentum, float* mean,
+                            float* invstd, float* running_mean, float* running_var, void* stream),
+       P2S_CHECK(s1 && s2 && mean && invstd && M > 0, "bad argument");
+        op_bn_finalize(s1, s2, M, C, eps, momentum, mean, invstd, running_mean, running_var, as_stream(stream)))
+P2S_OP(p2s_op_bn_apply, (const float* z, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int relu, float* y, void* stream),
+       P2S_CHECK(z && mean && invstd && gamma && beta && y, "null argument");
+        op_bn_apply(z, M, C, mean, invstd, gamma, beta, relu != 0, y, as_stream(stream)))
+P2S_OP(p2s_op_bn_backward, (const float* dy, const float* z, const float* y, int64_t M, int C, const float* mean,
+                            const float* invstd, const float* gamma, double* s1, double* s2, float* dz, void* stream),
+       P2S_CHECK(dy && z && mean && invstd && gamma && s1 && s2 && dz, "null argument");
+        op_bn_backward(dy, z, y, M, C, mean, invstd, gamma, s1, s2, dz, as_stream(stream)))
+P2S_OP(p2s_op_maxpool_fwd, (const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, void* stream),
+       P2S_CHECK(y && out && arg && npts > 0, "bad argument"); op_maxpool_fwd(y, B, npts, C, out, arg, as_stream(stream)))
+P2S_OP(p2s_op_maxpool_bwd, (const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, void* stream),
+       P2S_CHECK(dout && arg && dy, "null argument"); op_maxpool_bwd(dout, arg, B, npts, C, dy, as_stream(stream)))
+P2S_OP(p2s_op_loss, (const float* pred, const float* target_mag, const float* radius, const float* target_sign, int64_t B,
+                     float w_mag, float w_sign, int fixed_radius, double* loss_out, float* dpred, void* stream),
+       P2S_CHECK(pred && target_mag && target_sign && loss_out && (radius || fixed_radius) && B > 0, "bad argument");
+        op_loss(pred, target_mag, radius, target_sign, B, w_mag, w_sign, fixed_radius != 0, loss_out, dpred, as_stream(stream)))
+P2S_OP(p2s_op_quat_to_rot, (const float* q4, float* R, int64_t B, void* stream),
+       P2S_CHECK(q4 && R, "null argument"); launch_quat_to_rot(q4, R, B, as_stream(stream)))
+P2S_OP(p2s_op_quat_to_rot_bwd, (const float* q4, const float* dR, int64_t B, float* dq, void* stream),
+       P2S_CHECK(q4 && dR && dq, "null argument"); op_quat_to_rot_bwd(q4, dR, B, dq, as_stream(stream)))
+P2S_OP(p2s_op_add_row, (float* x, const float* v, int64_t B, int C, void* stream),
+       P2S_CHECK(x && v, "null argument"); op_add_row(x, v, B, C, as_stream(stream)))
+P2S_OP(p2s_op_center, (const float* in, const float* q, int64_t B, int npts, float* out, void* stream),
+       P2S_CHECK(in && q && out, "null argument"); op_center(in, q, B, npts, out, as_stream(stream)))
+P2S_OP(p2s_op_axpy, (float* y, const float* x, float a, int64_t n, void* stream),
+       P2S_CHECK(y && x, "null argument"); op_axpy(y, x, a, n, as_stream(stream)))
+P2S_OP(p2s_op_sgd, (float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum, int first_step,
+                    void* stream),
+       P2S_CHECK(param && grad && momentum_buf, "null argument");
+        op_sgd(param, grad, momentum_buf, n, lr, momentum, first_step != 0, as_stream(stream)))
+#undef P2S_OP
+
 }  // extern "C"

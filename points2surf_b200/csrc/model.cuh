@@ -78,6 +78,27 @@ void mesh_sample(const float* verts, int64_t V, const int32_t* faces, int64_t F,
                  float* samples, int32_t* face_ids, cudaStream_t st);
 void nn_distance(const float* a, int64_t na, const float* b, int64_t nb, float* dist, int32_t* idx, cudaStream_t st);
 void chamfer_hausdorff(const float* a, int64_t na, const float* b, int64_t nb, double* out4_host, cudaStream_t st);
+// train_ops.cu
+void op_gemm_tn(const float* A, int64_t a_stride_z, int lda, const float* B, int64_t b_stride_z, int ldb, float* C,
+                int64_t c_stride_z, int ldc, int M, int N, int K, int batch, bool accumulate, cudaStream_t st);
+void op_transpose(const float* in, float* out, int rows, int cols, int batch, cudaStream_t st);
+void op_col_stats(const float* x, int64_t M, int C, double* s1, double* s2, cudaStream_t st);
+void op_col_sum(const float* x, int64_t M, int C, double* s1, cudaStream_t st);
+void op_bn_finalize(const double* s1, const double* s2, int64_t M, int C, float eps, float momentum, float* mean,
+                    float* invstd, float* running_mean, float* running_var, cudaStream_t st);
+void op_bn_apply(const float* z, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, bool relu, float* y, cudaStream_t st);
+void op_bn_backward(const float* dy, const float* z, const float* y_or_null, int64_t M, int C, const float* mean,
+                    const float* invstd, const float* gamma, double* s1, double* s2, float* dz, cudaStream_t st);
+void op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, cudaStream_t st);
+void op_maxpool_bwd(const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, cudaStream_t st);
+void op_loss(const float* pred, const float* target_mag, const float* radius, const float* target_sign, int64_t B,
+             float w_mag, float w_sign, bool fixed_radius, double* loss_out, float* dpred, cudaStream_t st);
+void op_quat_to_rot_bwd(const float* q4, const float* dR, int64_t B, float* dq, cudaStream_t st);
+void op_add_row(float* x, const float* v, int64_t B, int C, cudaStream_t st);
+void op_sgd(float* p, const float* g, float* buf, int64_t n, float lr, float momentum, bool first, cudaStream_t st);
+void op_axpy(float* y, const float* x, float a, int64_t n, cudaStream_t st);
+void op_center(const float* in, const float* q, int64_t B, int npts, float* out, cudaStream_t st);
 // dispatch (api.cu)
 void forward(Model& m, const float* patch, const float* sub, const float* query, int64_t B,
              float* logits, cudaStream_t st);

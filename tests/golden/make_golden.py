@@ -218,8 +218,81 @@ def gen_evaluation():
     print('evaluation.npz written')
 
 
+TRAIN_SEEDS = {'vanilla': 21, 'max': 22, 'uniform': 23}
+
+
+def train_digest_indices(name, numel, count=48):
+    """Deterministic sample positions inside a tensor (shared with tests/helpers.py)."""
+    h = 2166136261
+    for ch in name.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return np.random.RandomState(h).randint(0, numel, size=min(count, numel))
+
+
+def gen_train():
+    """One training iteration of the UNMODIFIED reference (PointsToSurfModel.train(), compute_loss, optim.SGD with
+    momentum 0.9, source/points_to_surf_train.py:406,441-461,537-563) on a seeded batch of 8 queries; the fixture
+    stores the batch, logits, losses and a digest (norm + sampled entries) of every gradient and updated tensor.
+    oracle/train_oracle.py must reproduce all of it (asserted here)."""
+    from oracle import train_oracle
+    from source import points_to_surf_train as ref_train
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers_train import make_train_batch
+    for variant, seed in TRAIN_SEEDS.items():
+        v = synth.VARIANTS[variant]
+        torch.manual_seed(0)
+        m = PointsToSurfModel(net_size_max=1024, num_points=300, output_dim=2, use_point_stn=v['use_point_stn'],
+                              use_feat_stn=1, sym_op='max', use_query_point=0, sub_sample_size=1000, do_augmentation=0,
+                              single_transformer=0, shared_transformation=v['shared_transformer'])
+        sd = synth.make_state_dict(variant, seed=seed)
+        m.load_state_dict(sd)
+        m.train()
+        batch = make_train_batch(8, 300, 1000, seed=seed)
+        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9)
+        opt.zero_grad()
+        bd = {k: t.clone() for k, t in batch.items()}
+        with torch.enable_grad():
+            pred = m(bd)
+            loss = ref_train.compute_loss(pred=pred, batch_data=bd, outputs=['imp_surf_magnitude', 'imp_surf_sign'],
+                                          output_loss_weights={'imp_surf_magnitude': 1.0, 'imp_surf_sign': 1.0},
+                                          fixed_radius=False)
+            sum(loss).backward()
+        grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        opt.step()
+        new_sd = {k: t.detach().clone() for k, t in m.state_dict().items()}
+        orc_out = train_oracle.train_iteration(sd, batch, v['use_point_stn'], v['shared_transformer'], lr=0.01, momentum=0.9)
+        assert np.allclose(orc_out['logits'].numpy(), pred.detach().numpy(), atol=2e-5), variant
+        assert abs(orc_out['losses'][0] - float(loss[0])) < 1e-6 and abs(orc_out['losses'][1] - float(loss[1])) < 1e-6
+        gscale = max(float(g.abs().max()) for g in grads.values())
+        for k, g in grads.items():
+            err = float((orc_out['grads'][k] - g).abs().max())
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * gscale, (variant, k, err, float(g.abs().max()))
+        for k, t in new_sd.items():
+            if k.endswith('num_batches_tracked'):
+                continue
+            assert float((orc_out['new_state'][k] - t).abs().max()) <= 1e-5 * (1 + float(t.abs().max())), (variant, k)
+        out = {k: t.numpy() for k, t in batch.items()}
+        out['logits'] = pred.detach().numpy()
+        out['losses'] = np.array([float(loss[0]), float(loss[1])])
+        names = sorted(grads)
+        out['names'] = np.array(names)
+        out['grad_norm'] = np.array([float(grads[k].double().norm()) for k in names])
+        out['grad_max'] = np.array([float(grads[k].abs().max()) for k in names])
+        out['grad_samples'] = np.stack([np.pad(grads[k].reshape(-1).numpy()[train_digest_indices(k, grads[k].numel())],
+                                               (0, 48 - min(48, grads[k].numel()))) for k in names])
+        out['new_samples'] = np.stack([np.pad(new_sd[k].reshape(-1).numpy()[train_digest_indices(k, new_sd[k].numel())],
+                                              (0, 48 - min(48, new_sd[k].numel()))) for k in names])
+        bn = sorted(k for k in new_sd if k.endswith('running_mean') or k.endswith('running_var'))
+        out['buffer_names'] = np.array(bn)
+        out['buffer_samples'] = np.stack([np.pad(new_sd[k].numpy()[train_digest_indices(k, new_sd[k].numel())],
+                                                 (0, 48 - min(48, new_sd[k].numel()))) for k in bn])
+        np.savez_compressed(os.path.join(HERE, 'train_%s.npz' % variant), **out)
+        print('train_%s.npz written: losses %s, oracle == reference' % (variant, out['losses']))
+
+
 if __name__ == '__main__':
     gen_grid()
+    gen_train()
     gen_evaluation()
     gen_volume()
     gen_assembly()

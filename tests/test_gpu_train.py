@@ -1,0 +1,179 @@
+"""GPU tests of the training step: the `p2s_op_*` primitives against plain torch ops on
+the same device, and one full iteration of points2surf_b200.train.TrainStep against the digest of the unmodified
+reference's iteration (tests/golden/train_*.npz) and against the CPU training oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_oracle
+from oracle.p2s_oracle import quat_to_rotmat
+from points2surf_b200 import synth
+from points2surf_b200.train import TrainStep, compute_loss
+from points2surf_b200.train_ops import CudaPrims
+from helpers import load_golden, TRAIN_SEEDS, check_train_digest
+from helpers_train import TorchPrims, make_train_batch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def close(a, b, rtol, what=''):
+    a, b = a.double().cpu(), b.double().cpu()
+    err = float((a - b).abs().max())
+    assert err <= rtol * (float(b.abs().max()) + 1e-30), (what, err, float(b.abs().max()))
+
+
+@pytest.mark.parametrize('M,N,K,Z', [(1, 1, 1, 1), (300, 64, 3, 1), (1000, 3, 64, 1), (5000, 128, 64, 1), (4097, 1024, 128, 1),
+                                     (37, 4, 256, 1), (300, 64, 64, 7), (1000, 3, 3, 5), (129, 4096, 256, 1)])
+def test_gemm_nt_and_tn(M, N, K, Z):
+    p = CudaPrims()
+    A = rnd(Z, M, K, seed=1) if Z > 1 else rnd(M, K, seed=1)
+    W = rnd(Z, N, K, seed=2) if Z > 1 else rnd(N, K, seed=2)
+    bias = rnd(N, seed=3)
+    ref = torch.matmul(A.double(), W.double().transpose(-1, -2)) + bias.double()
+    close(p.gemm_nt(A, W, bias), ref, 2e-6 * max(1, K ** 0.5), 'nt')
+    close(p.gemm_nt(A, W, bias, relu=True), torch.relu(ref), 2e-6 * max(1, K ** 0.5), 'nt relu')
+    Bm = rnd(Z, M, N, seed=4) if Z > 1 else rnd(M, N, seed=4)     # dZ [M,N], X = A [M,K]
+    ref_tn = torch.matmul(Bm.double().transpose(-1, -2), A.double())
+    close(p.gemm_tn(Bm, A), ref_tn, 3e-6 * max(1, M ** 0.5), 'tn')
+    close(p.transpose(A), A.transpose(-1, -2), 0.0, 'transpose')
+
+
+def test_gemm_tn_split_reduction_large_m():
+    p = CudaPrims()
+    A, Bm = rnd(200000, 64, seed=5), rnd(200000, 128, seed=6)
+    close(p.gemm_tn(A, Bm), A.double().t() @ Bm.double(), 1e-4, 'tn large M')
+
+
+@pytest.mark.parametrize('M,C,relu', [(5, 512, True), (1300 * 6, 64, True), (3000, 1024, False), (2, 3, True), (70000, 128, True)])
+def test_batchnorm_forward_backward(M, C, relu):
+    p = CudaPrims()
+    z = rnd(M, C, seed=7, scale=2.0) + 0.5
+    gamma, beta = rnd(C, seed=8) * 0.2 + 1.0, rnd(C, seed=9) * 0.1
+    rm, rv = rnd(C, seed=10) * 0.1, torch.rand(C, device=DEV) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y, mean, invstd = p.bn_forward(z, gamma, beta, relu, rm, rv)
+    zt = z.double().requires_grad_(True)
+    gt, bt = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yr = torch.nn.functional.batch_norm(zt, rm_ref.double(), rv_ref.double(), gt, bt, training=True, momentum=0.1, eps=1e-5)
+    yr = torch.relu(yr) if relu else yr
+    close(y, yr.detach(), 1e-5, 'bn y')
+    close(rm, rm_ref.double() * 0 + (0.9 * rm_ref.double() + 0.1 * z.double().mean(0)), 1e-5, 'running mean')
+    if M > 1:
+        close(rv, 0.9 * rv_ref.double() + 0.1 * z.double().var(0, unbiased=True), 1e-5, 'running var')
+    dy = rnd(M, C, seed=11)
+    yr.backward(dy.double())
+    dz, dgamma, dbeta = p.bn_backward(dy, z, y if relu else None, mean, invstd, gamma)
+    tol = 2e-4 if M > 4 else 5e-2       # tiny batches: invstd ~ 1/sqrt(eps)-amplified rounding
+    close(dz, zt.grad, tol, 'bn dz')
+    close(dgamma, gt.grad, tol, 'dgamma')
+    close(dbeta, bt.grad, tol, 'dbeta')
+    close(p.col_sum(dy), dy.double().sum(0), 1e-5, 'col_sum')
+
+
+@pytest.mark.parametrize('B,n,C', [(3, 300, 1024), (5, 1000, 64), (1, 1, 7), (9, 1300, 128)])
+def test_maxpool_forward_backward(B, n, C):
+    p = CudaPrims()
+    y = rnd(B * n, C, seed=12)
+    out, arg = p.maxpool_fwd(y, B, n)
+    vr, ar = y.view(B, n, C).max(dim=1)
+    assert torch.equal(out, vr) and torch.equal(arg.long(), ar)
+    dout = rnd(B, C, seed=13)
+    dy = p.maxpool_bwd(dout, arg, n)
+    ref = torch.zeros(B, n, C, device=DEV).scatter_(1, ar.unsqueeze(1), dout.unsqueeze(1))
+    assert torch.equal(dy.view(B, n, C), ref)
+    # ReLU plateaus: ties resolve to the first maximum, like torch.max / MaxPool1d
+    yt = torch.relu(y - 2.5)
+    _, arg_t = p.maxpool_fwd(yt, B, n)
+    assert torch.equal(arg_t.long(), yt.view(B, n, C).max(dim=1)[1]) or True   # torch does not promise first-index on CUDA
+    first = (yt.view(B, n, C) == yt.view(B, n, C).max(dim=1, keepdim=True)[0]).float().argmax(dim=1)
+    assert torch.equal(arg_t.long(), first)
+
+
+def test_loss_quaternion_and_elementwise_ops():
+    p, tp = CudaPrims(), TorchPrims()
+    B = 1024
+    pred = rnd(B, 2, seed=14, scale=2.0)
+    pred[0, 0] = 0.0
+    tmag, rad = torch.rand(B, device=DEV) * 0.1, torch.rand(B, device=DEV) * 0.3 + 0.05
+    tsign = (torch.rand(B, device=DEV) < 0.5).float()
+    for fixed in (False, True):
+        ls, dp = p.loss(pred, tmag, rad, tsign, 1.0, 0.7, fixed_radius=fixed)
+        lr_, dr = tp.loss(pred.cpu(), tmag.cpu(), rad.cpu(), tsign.cpu(), 1.0, 0.7, fixed_radius=fixed)
+        close(ls, lr_, 1e-5, 'loss')
+        close(dp, dr, 1e-4, 'dloss')
+    q = rnd(B, 4, seed=15, scale=0.3)
+    R = p.quat_to_rot(q)
+    close(R, quat_to_rotmat((q + q.new_tensor([1, 0, 0, 0])).double()), 1e-5, 'quat_to_rot')
+    dR = rnd(B, 9, seed=16)
+    close(p.quat_to_rot_bwd(q, dR), tp.quat_to_rot_bwd(q.double().cpu(), dR.double().cpu()), 1e-4, 'quat bwd')
+    x, v = rnd(B, 64, seed=17), rnd(64, seed=18)
+    close(p.add_row_(x.clone(), v), x + v, 0.0, 'add_row')
+    pts, qq = rnd(7, 1000, 3, seed=19), rnd(7, 3, seed=20)
+    close(p.center(pts, qq), pts - qq.unsqueeze(1), 0.0, 'center')
+    yv = x.clone()
+    close(p.axpy_(yv, x, 0.5), x * 1.5, 1e-7, 'axpy')
+    par, grad, buf = rnd(1000, seed=21), rnd(1000, seed=22), torch.zeros(1000, device=DEV)
+    par0 = par.clone()
+    p.sgd_(par, grad, buf, 0.01, 0.9, True)
+    close(par, par0 - 0.01 * grad, 1e-6, 'sgd first')
+    p.sgd_(par, grad, buf, 0.01, 0.9, False)
+    close(par, par0 - 0.01 * grad - 0.01 * 1.9 * grad, 1e-6, 'sgd second')
+
+
+def _cuda_batch(batch):
+    return {k: t.to(DEV) for k, t in batch.items()}
+
+
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_train_iteration_matches_reference_digest(variant):
+    # fp32 CUDA iteration vs the reference's fp32 CPU iteration on the same 8-query batch.  Tolerance: 5e-3 of each
+    # tensor's largest gradient entry + 1e-4 of the globally largest (8-row BatchNorm statistics in the FC tails
+    # amplify summation-order differences); sign of every sampled entry must agree where it is above the floor.
+    g = load_golden('train_%s.npz' % variant)
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict(variant, seed=TRAIN_SEEDS[variant])
+    keys = ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms', 'patch_radius_ms', 'imp_surf_magnitude_ms',
+            'imp_surf_dist_sign_ms')
+    batch = {k: torch.from_numpy(g[k]).to(DEV) for k in keys}
+    ts = TrainStep({k: t.to(DEV) for k, t in sd.items()}, v['use_point_stn'], v['shared_transformer'], lr=0.01, momentum=0.9)
+    losses = ts.step(batch)
+    grads = {k: t.cpu() for k, t in ts.named_gradients().items()}
+    new = {k: t.cpu() for k, t in ts.state_dict().items()}
+    worst = check_train_digest(variant, grads, new, [float(l) for l in losses], ts.last_logits.cpu().numpy(), rtol=5e-3, floor=1e-4)
+    print(variant, 'worst gradient digest error (relative to tensor max):', worst)
+
+
+def test_train_two_steps_match_cpu_oracle_and_feed_inference():
+    # 32 queries, two iterations (momentum path), all tensors compared with the CPU oracle; then the trained
+    # state_dict drives the inference engine (the train -> eval hand-over of the reference, train.py:512-517)
+    from points2surf_b200 import ops
+    variant = 'vanilla'
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict(variant, seed=31)
+    b1, b2 = make_train_batch(32, seed=5), make_train_batch(32, seed=6)
+    r1 = train_oracle.train_iteration(sd, b1, 1, 1)
+    sd2 = dict(sd)
+    sd2.update(r1['new_state'])
+    r2 = train_oracle.train_iteration(sd2, b2, 1, 1, mom_bufs=r1['mom_bufs'])
+    ts = TrainStep({k: t.to(DEV) for k, t in sd.items()}, 1, 1)
+    l1 = ts.step(_cuda_batch(b1))
+    l2 = ts.step(_cuda_batch(b2))
+    assert abs(float(l1[0]) - r1['losses'][0]) < 2e-3 * r1['losses'][0] and abs(float(l2[1]) - r2['losses'][1]) < 2e-3 * r2['losses'][1]
+    new = ts.state_dict()
+    gscale = max(float(g.abs().max()) for g in r2['grads'].values())
+    for name, r in r2['new_state'].items():
+        err = float((new[name].cpu() - r).abs().max())
+        assert err <= 0.01 * 1.9 * (5e-3 * gscale) + 1e-4 * float(r.abs().max()) + 1e-6, (name, err)
+    eng = ops.Engine({k: t.cpu() for k, t in new.items()}, 1, 1, precision='fp32')
+    inp = synth.make_model_inputs(4, seed=9)
+    out = eng.forward(*(torch.from_numpy(inp[k]).to(DEV) for k in ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms')))
+    assert torch.isfinite(out).all()
+    with pytest.raises(ValueError):
+        ts.forward({'patch_pts_ps': torch.zeros(2, 10, 3, device=DEV), 'pts_sub_sample_ms': torch.zeros(2, 1000, 3, device=DEV),
+                    'imp_surf_query_point_ms': torch.zeros(2, 3, device=DEV)})

@@ -107,3 +107,20 @@ def test_marching_cubes_oracle_handles_zeros_and_noise():
     assert mc.mesh_is_closed(f) and np.isfinite(v).all()
     v2, f2 = mc.marching_cubes(np.full((8, 8, 8), -1.0, np.float32))
     assert len(v2) == 0 and len(f2) == 0
+
+
+@pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])
+def test_train_oracle_reproduces_reference_iteration(variant):
+    """oracle/train_oracle.py against the digest of one training iteration of the unmodified reference
+    (tests/golden/train_*.npz: losses, logits, every gradient, updated parameters, BatchNorm running statistics)."""
+    import torch
+    from oracle import train_oracle
+    from helpers import TRAIN_SEEDS, check_train_digest
+    g = load_golden('train_%s.npz' % variant)
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict(variant, seed=TRAIN_SEEDS[variant])
+    keys = ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms', 'patch_radius_ms', 'imp_surf_magnitude_ms',
+            'imp_surf_dist_sign_ms')
+    batch = {k: torch.from_numpy(g[k]) for k in keys}
+    out = train_oracle.train_iteration(sd, batch, v['use_point_stn'], v['shared_transformer'], lr=0.01, momentum=0.9)
+    check_train_digest(variant, out['grads'], out['new_state'], out['losses'], out['logits'].numpy(), rtol=2e-3, floor=2e-5)
