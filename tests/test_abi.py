@@ -76,3 +76,15 @@ def test_ply_off_roundtrip(tmp_path):
     mesh_io.write_off(str(tmp_path / 'q.off'), v, np.array([]), colors_vertex=np.random.rand(7, 3))
     lines = (tmp_path / 'q.off').read_text().split('\n')
     assert lines[0] == 'COFF' and lines[1] == '7 0 0' and len(lines[2].split()) == 6
+
+
+def test_library_is_newer_than_its_sources():
+    """A stale libp2s_b200.so travelling to the GPU box silently tests old kernels: rebuild with
+    `python -m points2surf_b200.build` whenever csrc/ or include/ changes."""
+    import glob
+    from points2surf_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    srcs = glob.glob(os.path.join(root, 'points2surf_b200', 'csrc', '*.cu*')) + glob.glob(os.path.join(root, 'include', '*.h'))
+    assert srcs
+    newest = max(os.path.getmtime(f) for f in srcs)
+    assert os.path.getmtime(_lib.LIB_PATH) >= newest, 'libp2s_b200.so is older than its sources'
