@@ -53,7 +53,7 @@ class TorchPrims:
 
     def maxpool_bwd(self, dout, arg, npts):
         B, C = dout.shape
-        dy = torch.zeros(B, npts, C, dtype=dout.dtype)
+        dy = torch.zeros(B, npts, C, dtype=dout.dtype, device=dout.device)
         dy.scatter_(1, arg.long().unsqueeze(1), dout.unsqueeze(1))
         return dy.view(B * npts, C)
 
