@@ -452,7 +452,11 @@ int p2s_chamfer_hausdorff_dev(const float* a, int64_t na, const float* b, int64_
 P2S_OP(p2s_op_gemm_nt, (const float* A, int64_t a_stride_z, int lda, const float* W, int64_t w_stride_z, const float* bias,
                         float* C, int64_t c_stride_z, int ldc, int M, int N, int K, int batch, int relu, void* stream),
        P2S_CHECK(A && W && C, "null argument");
-        launch_gemm_nt(A, a_stride_z, lda, W, w_stride_z, bias, C, c_stride_z, ldc, M, N, K, batch, relu != 0, as_stream(stream)))
+       // large unbatched shapes run on the tensor cores in split precision (fp32-level accuracy), the rest on fp32 FMA
+       if (batch == 1 && gemm_nt_tc_ok(A, lda, C, ldc, M, N, K))
+           launch_gemm_nt_tc(A, lda, W, bias, C, ldc, M, N, K, relu != 0, as_stream(stream));
+       else
+           launch_gemm_nt(A, a_stride_z, lda, W, w_stride_z, bias, C, c_stride_z, ldc, M, N, K, batch, relu != 0, as_stream(stream)))
 P2S_OP(p2s_op_gemm_tn, (const float* A, int64_t a_stride_z, int lda, const float* B, int64_t b_stride_z, int ldb, float* C,
                         int64_t c_stride_z, int ldc, int M, int N, int K, int batch, int accumulate, void* stream),
        P2S_CHECK(A && B && C, "null argument");

@@ -232,4 +232,34 @@ uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs
     return (uint8_t*)p;
 }
 
+// Split-precision tensor-core GEMM for weights that change between calls (training): packs W [N][K] into a reusable
+// scratch image on `st`, then runs fc_tc_kernel.  Stream order makes the scratch reuse safe.  bias may be null.
+bool gemm_nt_tc_ok(const float* A, int lda, const float* C, int ldc, int64_t M, int N, int K) {
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("P2S_TRAIN_GEMM_FP32");
+        disabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    return !disabled && fc_tc_supported(N, K) && N <= 4096 && M >= 512 && M < (int64_t)1 << 31 && lda % 4 == 0 && ldc % 4 == 0 &&
+           ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
+}
+
+void launch_gemm_nt_tc(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int64_t M, int N,
+                       int K, bool relu, cudaStream_t st) {
+    static thread_local DevBuf img, zeros;
+    static thread_local bool zeroed = false;
+    fc_tc_init();
+    uint8_t* wimg = reinterpret_cast<uint8_t*>(img.get((size_t)N * K * 4));
+    if (!bias) {
+        float* z = zeros.as<float>(4096);
+        if (!zeroed) {
+            P2S_CUDA(cudaMemsetAsync(z, 0, 4096 * sizeof(float), st));
+            zeroed = true;
+        }
+        bias = z;
+    }
+    P2S_LAUNCH(pack_fc_kernel, (unsigned)cdiv((int64_t)N * K, 256), 256, 0, st, W, N, K, wimg);
+    launch_fc_tc(A, lda, wimg, bias, C, ldc, M, N, K, relu, st, 0);
+}
+
 }  // namespace p2s

@@ -73,6 +73,9 @@ void fc_tc_init();
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
                   int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img = 0);
 uint8_t* fc_tc_pack_raw(const float* W, int N, int K, std::vector<void*>& allocs);
+bool gemm_nt_tc_ok(const float* A, int lda, const float* C, int ldc, int64_t M, int N, int K);
+void launch_gemm_nt_tc(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int64_t M, int N,
+                       int K, bool relu, cudaStream_t st);
 // meshdist.cu
 void mesh_sample(const float* verts, int64_t V, const int32_t* faces, int64_t F, int64_t n, uint64_t seed,
                  float* samples, int32_t* face_ids, cudaStream_t st);

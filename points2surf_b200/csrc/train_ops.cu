@@ -106,6 +106,7 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ z, cons
     if (c < C) {
         float mu = 0.f, is = 0.f;
         if (MODE == 1) { mu = mean[c]; is = invstd[c]; }
+#pragma unroll 4
         for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
             const int64_t e = r * C + c;
             float v = x[e];
@@ -194,15 +195,17 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ y, int64_t B, int n
     arg[e] = bi;
 }
 
+// grid (ceil(C / 256), point chunks, B): no integer division per element
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ arg, int64_t B, int npts,
                                    int C, float* __restrict__ dy) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * npts * C) return;
-    int c = (int)(e % C);
-    int64_t bp = e / C;
-    int p = (int)(bp % npts);
-    int64_t b = bp / npts;
-    dy[e] = (arg[b * C + c] == p) ? dout[b * C + c] : 0.f;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t b = blockIdx.z;
+    const int a = arg[b * C + c];
+    const float g = dout[b * C + c];
+    const int p0 = blockIdx.y * 32, p1 = min(npts, p0 + 32);
+    float* d = dy + (b * npts + p0) * (int64_t)C + c;
+    for (int p = p0; p < p1; ++p, d += C) *d = (p == a) ? g : 0.f;
 }
 
 // ---------------------------------------------------------------- loss (sdf_nn.calc_loss_magnitude / calc_loss_sign)
@@ -411,7 +414,8 @@ void op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int3
 
 void op_maxpool_bwd(const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, cudaStream_t st) {
     if (B <= 0) return;
-    P2S_LAUNCH(maxpool_bwd_kernel, (unsigned)cdiv(B * npts * C, 256), 256, 0, st, dout, arg, B, npts, C, dy);
+    P2S_CHECK(B <= 65535, "maxpool_bwd: batch too large for grid.z");
+    P2S_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)cdiv(C, 256), (unsigned)cdiv(npts, 32), (unsigned)B), 256, 0, st, dout, arg, B, npts, C, dy);
 }
 
 void op_loss(const float* pred, const float* target_mag, const float* radius, const float* target_sign, int64_t B,
