@@ -223,6 +223,14 @@ int p2s_op_bn_apply(const float* z, int64_t M, int C, const float* mean, const f
  * s2 = dgamma (f64 [C]) */
 int p2s_op_bn_backward(const float* dy, const float* z, const float* y, int64_t M, int C, const float* mean,
                        const float* invstd, const float* gamma, double* s1, double* s2, float* dz, void* stream);
+/* BatchNorm(train)(+ReLU) fused with the max over the npts points of each query (the conv3 layers): forward from the
+ * pre-BN z [B*npts, C] with mean / invstd from p2s_op_col_stats + p2s_op_bn_finalize; backward builds dz directly
+ * from dout [B,C] (s1 = dbeta, s2 = dgamma, f64 [C]) */
+int p2s_op_bn_maxpool_fwd(const float* z, int64_t B, int npts, int C, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, int relu, float* out, int32_t* arg, void* stream);
+int p2s_op_bn_maxpool_bwd(const float* dout, const int32_t* arg, const float* out, const float* z, int64_t B,
+                          int npts, int C, const float* mean, const float* invstd, const float* gamma, int relu,
+                          double* s1, double* s2, float* dz, void* stream);
 /* MaxPool1d over the npts points of each query: y [B, npts, C] -> out [B, C], arg [B, C] (first maximum) */
 int p2s_op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, void* stream);
 int p2s_op_maxpool_bwd(const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, void* stream);

@@ -479,6 +479,15 @@ P2S_OP(p2s_op_bn_backward, (const float* dy, const float* z, const float* y, int
                             const float* invstd, const float* gamma, double* s1, double* s2, float* dz, void* stream),
        P2S_CHECK(dy && z && mean && invstd && gamma && s1 && s2 && dz, "null argument");
         op_bn_backward(dy, z, y, M, C, mean, invstd, gamma, s1, s2, dz, as_stream(stream)))
+P2S_OP(p2s_op_bn_maxpool_fwd, (const float* z, int64_t B, int npts, int C, const float* mean, const float* invstd,
+                               const float* gamma, const float* beta, int relu, float* out, int32_t* arg, void* stream),
+       P2S_CHECK(z && mean && invstd && gamma && beta && out && arg && npts > 0, "bad argument");
+        op_bn_maxpool_fwd(z, B, npts, C, mean, invstd, gamma, beta, relu != 0, out, arg, as_stream(stream)))
+P2S_OP(p2s_op_bn_maxpool_bwd, (const float* dout, const int32_t* arg, const float* out, const float* z, int64_t B, int npts, int C,
+                               const float* mean, const float* invstd, const float* gamma, int relu, double* s1, double* s2,
+                               float* dz, void* stream),
+       P2S_CHECK(dout && arg && out && z && mean && invstd && gamma && s1 && s2 && dz && npts > 0, "bad argument");
+        op_bn_maxpool_bwd(dout, arg, out, z, B, npts, C, mean, invstd, gamma, relu != 0, s1, s2, dz, as_stream(stream)))
 P2S_OP(p2s_op_maxpool_fwd, (const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, void* stream),
        P2S_CHECK(y && out && arg && npts > 0, "bad argument"); op_maxpool_fwd(y, B, npts, C, out, arg, as_stream(stream)))
 P2S_OP(p2s_op_maxpool_bwd, (const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, void* stream),

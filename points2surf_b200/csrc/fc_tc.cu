@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             } else if (row < M) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
+                    if (nt * 128 + n0 + j >= N) continue;   // padded tile (N % 128 != 0, N % 4 == 0)
                     float4 o;
                     o.x = __uint_as_float(r[j + 0]) + b[n0 + j + 0];
                     o.y = __uint_as_float(r[j + 1]) + b[n0 + j + 1];
@@ -193,6 +194,19 @@ __global__ void pack_fc_kernel(const float* __restrict__ W, int N, int K, uint8_
     *reinterpret_cast<__half*>(img + off + kHalf) = __float2half_rn(w - __half2float(h));
 }
 
+// same image for N rows padded with zeros to Npad (multiple of 128)
+__global__ void pack_fc_pad_kernel(const float* __restrict__ W, int N, int Npad, int K, uint8_t* __restrict__ img) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)Npad * K) return;
+    int n = (int)(e / K), k = (int)(e % K);
+    int nt = n >> 7, r = n & 127, kt = k / kBK, kk = k % kBK;
+    size_t off = ((size_t)nt * (K / kBK) + kt) * kStageB + (size_t)(r >> 3) * 512 + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+    const float w = n < N ? W[e] : 0.f;
+    const __half h = __float2half_rn(w);
+    *reinterpret_cast<__half*>(img + off) = h;
+    *reinterpret_cast<__half*>(img + off + kHalf) = __float2half_rn(w - __half2float(h));
+}
+
 }  // namespace
 
 bool fc_tc_supported(int N, int K) { return (N % 128 == 0) && (K % kBK == 0) && N >= 128 && K >= kBK; }
@@ -217,8 +231,9 @@ void fc_tc_init() {
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
                   int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img) {
     if (M <= 0) return;
-    P2S_CHECK(fc_tc_supported(N, K) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
-    dim3 grid((unsigned)cdiv(M, 128), (unsigned)(N / 128), 1);
+    const bool padded_ok = !pack_img && N % 4 == 0 && N >= 64 && K % kBK == 0;   // partial last N tile (training GEMMs)
+    P2S_CHECK((fc_tc_supported(N, K) || padded_ok) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
+    dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 128), 1);
     P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img);
 }
 
@@ -240,7 +255,7 @@ bool gemm_nt_tc_ok(const float* A, int lda, const float* C, int ldc, int64_t M, 
         const char* e = getenv("P2S_TRAIN_GEMM_FP32");
         disabled = (e && e[0] == '1') ? 1 : 0;
     }
-    return !disabled && fc_tc_supported(N, K) && N <= 4096 && M >= 512 && M < (int64_t)1 << 31 && lda % 4 == 0 && ldc % 4 == 0 &&
+    return !disabled && N % 4 == 0 && N >= 64 && K % kBK == 0 && K >= kBK && N <= 4096 && M >= 512 && M < (int64_t)1 << 31 && lda % 4 == 0 && ldc % 4 == 0 &&
            ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
 }
 
@@ -249,7 +264,8 @@ void launch_gemm_nt_tc(const float* A, int lda, const float* W, const float* bia
     static thread_local DevBuf img, zeros;
     static thread_local bool zeroed = false;
     fc_tc_init();
-    uint8_t* wimg = reinterpret_cast<uint8_t*>(img.get((size_t)N * K * 4));
+    const int Npad = (int)(cdiv(N, 128) * 128);
+    uint8_t* wimg = reinterpret_cast<uint8_t*>(img.get((size_t)Npad * K * 4));
     if (!bias) {
         float* z = zeros.as<float>(4096);
         if (!zeroed) {
@@ -258,7 +274,7 @@ void launch_gemm_nt_tc(const float* A, int lda, const float* W, const float* bia
         }
         bias = z;
     }
-    P2S_LAUNCH(pack_fc_kernel, (unsigned)cdiv((int64_t)N * K, 256), 256, 0, st, W, N, K, wimg);
+    P2S_LAUNCH(pack_fc_pad_kernel, (unsigned)cdiv((int64_t)Npad * K, 256), 256, 0, st, W, N, Npad, K, wimg);
     launch_fc_tc(A, lda, wimg, bias, C, ldc, M, N, K, relu, st, 0);
 }
 

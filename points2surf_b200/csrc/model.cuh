@@ -93,6 +93,11 @@ void op_bn_apply(const float* z, int64_t M, int C, const float* mean, const floa
                  const float* beta, bool relu, float* y, cudaStream_t st);
 void op_bn_backward(const float* dy, const float* z, const float* y_or_null, int64_t M, int C, const float* mean,
                     const float* invstd, const float* gamma, double* s1, double* s2, float* dz, cudaStream_t st);
+void op_bn_maxpool_fwd(const float* z, int64_t B, int npts, int C, const float* mean, const float* invstd,
+                       const float* gamma, const float* beta, bool relu, float* out, int32_t* arg, cudaStream_t st);
+void op_bn_maxpool_bwd(const float* dout, const int32_t* arg, const float* out, const float* z, int64_t B, int npts, int C,
+                       const float* mean, const float* invstd, const float* gamma, bool relu, double* s1, double* s2,
+                       float* dz, cudaStream_t st);
 void op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, cudaStream_t st);
 void op_maxpool_bwd(const float* dout, const int32_t* arg, int64_t B, int npts, int C, float* dy, cudaStream_t st);
 void op_loss(const float* pred, const float* target_mag, const float* radius, const float* target_sign, int64_t B,

@@ -149,32 +149,125 @@ __global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* 
     }
 }
 
+// Row-tiled element-wise kernels: blockDim = (tx, 256 / tx) with tx consecutive channels per row, grid = (channel
+// blocks, row chunks); every thread keeps the parameters of its channel in registers and walks down the rows, so the
+// accesses are coalesced and there is no per-element integer division.
 // y = act(gamma * (z - mean) * invstd + beta)
-__global__ void bn_apply_kernel(const float* __restrict__ z, int64_t total, int C, const float* __restrict__ mean,
-                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int relu, float* __restrict__ y) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    int c = (int)(e % C);
-    float v = fmaf(gamma[c] * invstd[c], z[e] - mean[c], beta[c]);
-    y[e] = relu ? fmaxf(v, 0.f) : v;
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ z, int64_t M, int C, int64_t rows_per_block, const float* __restrict__ mean,
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int relu, float* __restrict__ y) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float a = gamma[c] * invstd[c], mu = mean[c], bt = beta[c];
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const float v = fmaf(a, z[r * C + c] - mu, bt);
+        y[r * C + c] = relu ? fmaxf(v, 0.f) : v;
+    }
 }
 
 // dz = gamma * invstd * (g - s1/M - xhat * s2/M), g = dy masked by the ReLU
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ z,
-                                    const float* __restrict__ y, int64_t total, int C, int64_t M,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const double* __restrict__ s1,
-                                    const double* __restrict__ s2, float* __restrict__ dz) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    int c = (int)(e % C);
-    float g = dy[e];
-    if (y && !(y[e] > 0.f)) g = 0.f;
-    float is = invstd[c];
-    float xhat = (z[e] - mean[c]) * is;
-    float m1 = (float)(s1[c] / (double)M), m2 = (float)(s2[c] / (double)M);
-    dz[e] = gamma[c] * is * (g - m1 - xhat * m2);
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ y, int64_t M,
+                    int C, int64_t rows_per_block, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, const double* __restrict__ s1, const double* __restrict__ s2,
+                    float* __restrict__ dz) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float is = invstd[c], mu = mean[c], gi = gamma[c] * is;
+    const float m1 = (float)(s1[c] / (double)M), m2 = (float)(s2[c] / (double)M);
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const int64_t e = r * C + c;
+        float g = dy[e];
+        if (y && !(y[e] > 0.f)) g = 0.f;
+        const float xhat = (z[e] - mu) * is;
+        dz[e] = gi * (g - m1 - xhat * m2);
+    }
+}
+
+// ---- BatchNorm (+ReLU) fused with the max over the points of each query (the conv3 layers: the 1024-channel
+// activations are never materialised after the BatchNorm, and the backward never builds the sparse dy)
+__global__ void bn_maxpool_fwd_kernel(const float* __restrict__ z, int64_t B, int npts, int C,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                      float* __restrict__ out, int32_t* __restrict__ arg) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (c >= C) return;
+    const float a = gamma[c] * invstd[c], mu = mean[c], bt = beta[c];
+    const float* p = z + b * npts * (int64_t)C + c;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int i = 0; i < npts; ++i) {
+        float v = fmaf(a, p[(int64_t)i * C] - mu, bt);
+        if (relu) v = fmaxf(v, 0.f);
+        if (v > best || i == 0) { best = v; bi = i; }   // first maximum, like torch.max / MaxPool1d
+    }
+    out[b * C + c] = best;
+    arg[b * C + c] = bi;
+}
+
+// s1[c] += sum_b g, s2[c] += sum_b g * xhat(b, arg, c); g = dout * (out > 0 if relu)
+__global__ void __launch_bounds__(256)
+bn_maxpool_bwd_reduce_kernel(const float* __restrict__ dout, const int32_t* __restrict__ arg,
+                             const float* __restrict__ out, const float* __restrict__ z,
+                             const float* __restrict__ mean, const float* __restrict__ invstd, int64_t B, int npts,
+                             int C, int relu, int64_t rows_per_block, double* __restrict__ s1, double* __restrict__ s2) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.y * rows_per_block, b1 = min(B, b0 + rows_per_block);
+    float a1 = 0.f, a2 = 0.f;
+    if (c < C) {
+        const float mu = mean[c], is = invstd[c];
+        for (int64_t b = b0 + threadIdx.y; b < b1; b += 8) {
+            float g = dout[b * C + c];
+            if (relu && !(out[b * C + c] > 0.f)) g = 0.f;
+            const float xhat = (z[(b * npts + arg[b * C + c]) * (int64_t)C + c] - mu) * is;
+            a1 += g;
+            a2 = fmaf(g, xhat, a2);
+        }
+    }
+    __shared__ float r1[8][32], r2[8][32];
+    r1[threadIdx.y][threadIdx.x] = a1;
+    r2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d1 += (double)r1[j][threadIdx.x]; d2 += (double)r2[j][threadIdx.x]; }
+        atomicAdd(s1 + c, d1);
+        atomicAdd(s2 + c, d2);
+    }
+}
+
+// grid (channel blocks, point chunks of 32, B)
+__global__ void __launch_bounds__(256)
+bn_maxpool_bwd_apply_kernel(const float* __restrict__ dout, const int32_t* __restrict__ arg,
+                            const float* __restrict__ out, const float* __restrict__ z, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                            const double* __restrict__ s1, const double* __restrict__ s2, int64_t B, int npts, int C,
+                            int relu, float* __restrict__ dz) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t b = blockIdx.z;
+    const int64_t M = B * npts;
+    const float is = invstd[c], mu = mean[c], gi = gamma[c] * is;
+    const float m1 = (float)(s1[c] / (double)M), m2 = (float)(s2[c] / (double)M);
+    const int a = arg[b * C + c];
+    float g = dout[b * C + c];
+    if (relu && !(out[b * C + c] > 0.f)) g = 0.f;
+    const int p0 = blockIdx.y * 32, p1 = min(npts, p0 + 32);
+    const int64_t base = (b * npts + p0) * (int64_t)C + c;
+    const float* zp = z + base;
+    float* dp = dz + base;
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p, zp += C, dp += C) {
+        const float xhat = (*zp - mu) * is;
+        *dp = gi * ((p == a ? g : 0.f) - m1 - xhat * m2);
+    }
 }
 
 // ---------------------------------------------------------------- max over the points of each query, with argmax
@@ -363,6 +456,17 @@ static void col_reduce_grid(int64_t M, int C, dim3& g, int64_t& rows_per_block) 
     g = dim3((unsigned)cx, (unsigned)cdiv(M, rows_per_block));
 }
 
+// blockDim (tx, 256/tx), grid (channel blocks, row chunks) for the row-tiled element-wise kernels
+static void rowwise_grid(int64_t M, int C, dim3& blk, dim3& g, int64_t& rows_per_block) {
+    const int tx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+    blk = dim3(tx, 256 / tx);
+    const int64_t cx = cdiv(C, tx);
+    const int64_t want = std::max<int64_t>(1, cdiv(16 * (int64_t)sm_count(), cx));
+    rows_per_block = std::max<int64_t>(4 * blk.y, cdiv(M, want));
+    rows_per_block = std::max<int64_t>(rows_per_block, cdiv(M, 65535));
+    g = dim3((unsigned)cx, (unsigned)cdiv(M, rows_per_block));
+}
+
 // s1, s2: f64 [C], zeroed here
 void op_col_stats(const float* x, int64_t M, int C, double* s1, double* s2, cudaStream_t st) {
     P2S_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * C, st));
@@ -390,8 +494,9 @@ void op_bn_finalize(const double* s1, const double* s2, int64_t M, int C, float 
 void op_bn_apply(const float* z, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
                  const float* beta, bool relu, float* y, cudaStream_t st) {
     if (M <= 0) return;
-    P2S_LAUNCH(bn_apply_kernel, (unsigned)cdiv(M * C, 256), 256, 0, st, z, M * C, C, mean, invstd, gamma, beta,
-               relu ? 1 : 0, y);
+    dim3 blk, g; int64_t rpb;
+    rowwise_grid(M, C, blk, g, rpb);
+    P2S_LAUNCH(bn_apply_kernel, g, blk, 0, st, z, M, C, rpb, mean, invstd, gamma, beta, relu ? 1 : 0, y);
 }
 
 // dz from dy; s1 (= dbeta) and s2 (= dgamma) f64 [C] are outputs
@@ -403,8 +508,9 @@ void op_bn_backward(const float* dy, const float* z, const float* y_or_null, int
     dim3 g; int64_t rpb;
     col_reduce_grid(M, C, g, rpb);
     P2S_LAUNCH(col_reduce_kernel<1>, g, dim3(32, 8), 0, st, dy, z, y_or_null, mean, invstd, M, C, rpb, s1, s2);
-    P2S_LAUNCH(bn_bwd_apply_kernel, (unsigned)cdiv(M * C, 256), 256, 0, st, dy, z, y_or_null, M * C, C, M, mean, invstd,
-               gamma, s1, s2, dz);
+    dim3 blk, g2; int64_t rpb2;
+    rowwise_grid(M, C, blk, g2, rpb2);
+    P2S_LAUNCH(bn_bwd_apply_kernel, g2, blk, 0, st, dy, z, y_or_null, M, C, rpb2, mean, invstd, gamma, s1, s2, dz);
 }
 
 void op_maxpool_fwd(const float* y, int64_t B, int npts, int C, float* out, int32_t* arg, cudaStream_t st) {
@@ -447,6 +553,31 @@ void op_axpy(float* y, const float* x, float a, int64_t n, cudaStream_t st) {
 void op_center(const float* in, const float* q, int64_t B, int npts, float* out, cudaStream_t st) {
     if (B <= 0) return;
     P2S_LAUNCH(center_kernel, (unsigned)cdiv(B * npts * 3, 256), 256, 0, st, in, q, B, npts, out);
+}
+
+// BatchNorm(train) (+ReLU) + max over the npts points of each query, without materialising the normalised tensor
+void op_bn_maxpool_fwd(const float* z, int64_t B, int npts, int C, const float* mean, const float* invstd,
+                       const float* gamma, const float* beta, bool relu, float* out, int32_t* arg, cudaStream_t st) {
+    if (B <= 0) return;
+    P2S_CHECK(B <= 65535, "bn_maxpool_fwd: batch too large for grid.y");
+    P2S_LAUNCH(bn_maxpool_fwd_kernel, dim3((unsigned)cdiv(C, 128), (unsigned)B), 128, 0, st, z, B, npts, C, mean, invstd,
+               gamma, beta, relu ? 1 : 0, out, arg);
+}
+
+// backward of the above: dout [B,C] -> dz [B*npts, C]; s1 = dbeta, s2 = dgamma (f64 [C])
+void op_bn_maxpool_bwd(const float* dout, const int32_t* arg, const float* out, const float* z, int64_t B, int npts, int C,
+                       const float* mean, const float* invstd, const float* gamma, bool relu, double* s1, double* s2,
+                       float* dz, cudaStream_t st) {
+    P2S_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * C, st));
+    P2S_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * C, st));
+    if (B <= 0) return;
+    P2S_CHECK(B <= 65535, "bn_maxpool_bwd: batch too large for grid.z");
+    const int64_t rpb = std::max<int64_t>(8, cdiv(B, 64));
+    P2S_LAUNCH(bn_maxpool_bwd_reduce_kernel, dim3((unsigned)cdiv(C, 32), (unsigned)cdiv(B, rpb)), dim3(32, 8), 0, st, dout, arg,
+               out, z, mean, invstd, B, npts, C, relu ? 1 : 0, rpb, s1, s2);
+    const int tx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+    P2S_LAUNCH(bn_maxpool_bwd_apply_kernel, dim3((unsigned)cdiv(C, tx), (unsigned)cdiv(npts, 32), (unsigned)B), tx, 0, st, dout,
+               arg, out, z, mean, invstd, gamma, s1, s2, B, npts, C, relu ? 1 : 0, dz);
 }
 
 }  // namespace p2s

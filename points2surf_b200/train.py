@@ -42,8 +42,8 @@ def compute_loss(pred, batch_data, outputs, output_loss_weights, fixed_radius, p
 
 
 class _Tape:
-    """Forward records of one linear(+BN)(+ReLU) unit."""
-    __slots__ = ('name', 'bn', 'x', 'z', 'y_mask', 'mean', 'invstd')
+    """Forward records of one linear(+BN)(+ReLU)(+max over points) unit."""
+    __slots__ = ('name', 'bn', 'x', 'z', 'y_mask', 'mean', 'invstd', 'pool', 'relu')
 
 
 class TrainStep:
@@ -110,7 +110,7 @@ class TrainStep:
         p = self.p
         z = p.gemm_nt(x, self.params[name + '.weight'], self.params[name + '.bias'])
         t = _Tape()
-        t.name, t.bn, t.x, t.z = name, bn, x, z
+        t.name, t.bn, t.x, t.z, t.pool, t.relu = name, bn, x, z, None, relu
         if bn is not None:
             y, t.mean, t.invstd = p.bn_forward(z, self.params[bn + '.weight'], self.params[bn + '.bias'], relu,
                                                self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'],
@@ -124,16 +124,37 @@ class TrainStep:
         tape.append(t)
         return y
 
+    def _lin_pool(self, tape, x, name, bn, relu, B, n):
+        """conv + BatchNorm (+ReLU) + max over the n points of each query; the normalised [B*n, C] tensor is never
+        materialised (model.py:45-48, 104-107, 203-212)."""
+        p = self.p
+        z = p.gemm_nt(x, self.params[name + '.weight'], self.params[name + '.bias'])
+        out, arg, mean, invstd = p.bn_maxpool_forward(z, B, n, self.params[bn + '.weight'], self.params[bn + '.bias'], relu,
+                                                      self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'],
+                                                      BN_EPS, BN_MOMENTUM)
+        self.buffers[bn + '.num_batches_tracked'] += 1
+        t = _Tape()
+        t.name, t.bn, t.x, t.z, t.y_mask, t.mean, t.invstd, t.pool, t.relu = name, bn, x, z, None, mean, invstd, (out, arg, B, n), relu
+        tape.append(t)
+        return out
+
     def _lin_bwd(self, t, dy, need_dx=True):
         p = self.p
-        if t.bn is not None:
+        if t.pool is not None:
+            out, arg, B, n = t.pool
+            dz, dgamma, dbeta = p.bn_maxpool_backward(dy, arg, out, t.z, t.mean, t.invstd, self.params[t.bn + '.weight'], t.relu, B, n)
+        elif t.bn is not None:
             dz, dgamma, dbeta = p.bn_backward(dy, t.z, t.y_mask, t.mean, t.invstd, self.params[t.bn + '.weight'])
-            p.axpy_(self.grads[t.bn + '.weight'], dgamma)
-            p.axpy_(self.grads[t.bn + '.bias'], dbeta)
         else:
             dz = dy
-        p.axpy_(self.grads[t.name + '.bias'], p.col_sum(dz))
-        p.axpy_(self.grads[t.name + '.weight'], p.gemm_tn(dz, t.x))
+        if t.bn is not None:
+            p.axpy_(self.grads[t.bn + '.weight'], dgamma)
+            p.axpy_(self.grads[t.bn + '.bias'], dbeta)
+            # the bias of a layer in front of a train-mode BatchNorm has an identically zero gradient (dz sums to zero
+            # over the rows by construction; torch's value is rounding noise): it stays 0
+        else:
+            p.axpy_(self.grads[t.name + '.bias'], p.col_sum(dz))
+        p.gemm_tn(dz, t.x, out=self.grads[t.name + '.weight'])
         if not need_dx:
             return None
         return p.gemm_nt(dz, p.transpose(self.params[t.name + '.weight']))
@@ -143,19 +164,17 @@ class TrainStep:
         tape = []
         h = self._lin(tape, x, prefix + 'conv1', prefix + 'bn1', True)
         h = self._lin(tape, h, prefix + 'conv2', prefix + 'bn2', True)
-        h = self._lin(tape, h, prefix + 'conv3', prefix + 'bn3', True)
-        g, arg = self.p.maxpool_fwd(h, B, n)
+        g = self._lin_pool(tape, h, prefix + 'conv3', prefix + 'bn3', True, B, n)
         f = self._lin(tape, g, prefix + 'fc1', prefix + 'bn4', True)
         f = self._lin(tape, f, prefix + 'fc2', prefix + 'bn5', True)
         out = self._lin(tape, f, prefix + 'fc3', None, False)
-        return out, (tape, arg, n)
+        return out, tape
 
     def _stn_bwd(self, ctx, dout, need_dx):
-        tape, arg, n = ctx
+        tape = ctx
         d = self._lin_bwd(tape[5], dout)
         d = self._lin_bwd(tape[4], d)
         d = self._lin_bwd(tape[3], d)
-        d = self.p.maxpool_bwd(d, arg, n)
         d = self._lin_bwd(tape[2], d)
         d = self._lin_bwd(tape[1], d)
         return self._lin_bwd(tape[0], d, need_dx)
@@ -171,15 +190,13 @@ class TrainStep:
         ht = p.gemm_nt(hb.view(B, n, 64), T).view(B * n, 64)          # torch.bmm(trans2, x), model.py:200
         h = self._lin(tape, ht, prefix + 'conv1', prefix + 'bn1', True)
         h = self._lin(tape, h, prefix + 'conv2', prefix + 'bn2', True)
-        h = self._lin(tape, h, prefix + 'conv3', prefix + 'bn3', False)
-        g, arg = p.maxpool_fwd(h, B, n)
-        return g, (tape, stn_ctx, T, hb, arg, B, n)
+        g = self._lin_pool(tape, h, prefix + 'conv3', prefix + 'bn3', False, B, n)
+        return g, (tape, stn_ctx, T, hb, B, n)
 
     def _feat_bwd(self, ctx, dg, need_dpts):
         p = self.p
-        tape, stn_ctx, T, hb, arg, B, n = ctx
-        d = p.maxpool_bwd(dg, arg, n)
-        d = self._lin_bwd(tape[4], d)
+        tape, stn_ctx, T, hb, B, n = ctx
+        d = self._lin_bwd(tape[4], dg)
         d = self._lin_bwd(tape[3], d)
         dht = self._lin_bwd(tape[2], d).view(B, n, 64)
         dhb = p.gemm_nt(dht, p.transpose(T)).view(B * n, 64)            # dx = T^T dy  (rows: dy_row T)

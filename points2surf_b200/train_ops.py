@@ -39,8 +39,8 @@ class CudaPrims:
                                           M * N, N, M, N, K, Z, 1 if relu else 0, _stream()))
         return out
 
-    def gemm_tn(self, A, B):
-        """A [M,N], B [M,K] (or batched [Z,M,*]) -> A^T B [N,K] (or [Z,N,K])."""
+    def gemm_tn(self, A, B, out=None):
+        """A [M,N], B [M,K] (or batched [Z,M,*]) -> A^T B [N,K] (or [Z,N,K]); with `out` the product is ADDED to it."""
         A, B = _f(A, 'A'), _f(B, 'B')
         batched = A.dim() == 3
         Z = A.shape[0] if batched else 1
@@ -48,9 +48,15 @@ class CudaPrims:
         K = B.shape[-1]
         if B.shape[-2] != M:
             raise P2SError('gemm_tn: M mismatch')
-        out = torch.empty((Z, N, K) if batched else (N, K), dtype=torch.float32, device=A.device)
+        acc = out is not None
+        if acc:
+            if not out.is_contiguous() or out.numel() != Z * N * K or out.dtype != torch.float32 or not out.is_cuda:
+                raise P2SError('gemm_tn: bad `out`')
+        else:
+            out = torch.empty((Z, N, K) if batched else (N, K), dtype=torch.float32, device=A.device)
         with torch.cuda.device(A.device):
-            check(self.lib.p2s_op_gemm_tn(_ptr(A), M * N, N, _ptr(B), M * K, K, _ptr(out), N * K, K, M, N, K, Z, 0, _stream()))
+            check(self.lib.p2s_op_gemm_tn(_ptr(A), M * N, N, _ptr(B), M * K, K, _ptr(out), N * K, K, M, N, K, Z, 1 if acc else 0,
+                                          _stream()))
         return out
 
     def transpose(self, x):
@@ -89,6 +95,36 @@ class CudaPrims:
             check(self.lib.p2s_op_bn_backward(_ptr(dy), _ptr(z), _ptr(_f(y_mask, 'y')) if y_mask is not None else None, M, Cc,
                                               _ptr(mean), _ptr(invstd), _ptr(_f(gamma, 'gamma')), _ptr(s[0]), _ptr(s[1]), _ptr(dz),
                                               _stream()))
+        return dz, s[1].float(), s[0].float()
+
+    def bn_maxpool_forward(self, z, B, npts, gamma, beta, relu, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+        """max over the points of act(BN_train(z)) without materialising it -> out [B,C], arg [B,C], mean, invstd."""
+        z = _f(z, 'z')
+        M, Cc = z.shape
+        s = torch.empty((2, Cc), dtype=torch.float64, device=z.device)
+        mean = torch.empty(Cc, dtype=torch.float32, device=z.device)
+        invstd = torch.empty_like(mean)
+        out = torch.empty((B, Cc), dtype=torch.float32, device=z.device)
+        arg = torch.empty((B, Cc), dtype=torch.int32, device=z.device)
+        with torch.cuda.device(z.device):
+            check(self.lib.p2s_op_col_stats(_ptr(z), M, Cc, _ptr(s[0]), _ptr(s[1]), _stream()))
+            check(self.lib.p2s_op_bn_finalize(_ptr(s[0]), _ptr(s[1]), M, Cc, float(eps), float(momentum), _ptr(mean), _ptr(invstd),
+                                              _ptr(running_mean) if running_mean is not None else None,
+                                              _ptr(running_var) if running_var is not None else None, _stream()))
+            check(self.lib.p2s_op_bn_maxpool_fwd(_ptr(z), B, npts, Cc, _ptr(mean), _ptr(invstd), _ptr(_f(gamma, 'gamma')),
+                                                 _ptr(_f(beta, 'beta')), 1 if relu else 0, _ptr(out), _ptr(arg), _stream()))
+        return out, arg, mean, invstd
+
+    def bn_maxpool_backward(self, dout, arg, out, z, mean, invstd, gamma, relu, B, npts):
+        """-> dz [B*npts, C], dgamma, dbeta."""
+        z = _f(z, 'z')
+        Cc = z.shape[1]
+        s = torch.empty((2, Cc), dtype=torch.float64, device=z.device)
+        dz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            check(self.lib.p2s_op_bn_maxpool_bwd(_ptr(_f(dout, 'dout')), _ptr(_dev(arg, torch.int32, 'arg')), _ptr(_f(out, 'out')), _ptr(z),
+                                                 B, npts, Cc, _ptr(mean), _ptr(invstd), _ptr(_f(gamma, 'gamma')), 1 if relu else 0,
+                                                 _ptr(s[0]), _ptr(s[1]), _ptr(dz), _stream()))
         return dz, s[1].float(), s[0].float()
 
     def col_sum(self, x):

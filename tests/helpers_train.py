@@ -17,8 +17,21 @@ class TorchPrims:
             out = out + bias
         return torch.relu(out) if relu else out
 
-    def gemm_tn(self, A, B):
-        return torch.matmul(A.transpose(-1, -2), B)
+    def gemm_tn(self, A, B, out=None):
+        r = torch.matmul(A.transpose(-1, -2), B)
+        return r if out is None else out.add_(r.reshape(out.shape))
+
+    def bn_maxpool_forward(self, z, B, npts, gamma, beta, relu, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+        y, mean, invstd = self.bn_forward(z, gamma, beta, relu, running_mean, running_var, eps, momentum)
+        out, arg = self.maxpool_fwd(y, B, npts)
+        return out, arg, mean, invstd
+
+    def bn_maxpool_backward(self, dout, arg, out, z, mean, invstd, gamma, relu, B, npts):
+        dy = self.maxpool_bwd(dout, arg, npts)
+        y = None
+        if relu:   # the mask only matters at the arg-max rows, where y == out
+            y = self.maxpool_bwd(out, arg, npts)
+        return self.bn_backward(dy, z, y, mean, invstd, gamma)
 
     def transpose(self, x):
         return x.transpose(-1, -2).contiguous()

@@ -29,7 +29,8 @@ def close(a, b, rtol, what=''):
 
 
 @pytest.mark.parametrize('M,N,K,Z', [(1, 1, 1, 1), (300, 64, 3, 1), (1000, 3, 64, 1), (5000, 128, 64, 1), (4097, 1024, 128, 1),
-                                     (37, 4, 256, 1), (300, 64, 64, 7), (1000, 3, 3, 5), (129, 4096, 256, 1)])
+                                     (37, 4, 256, 1), (300, 64, 64, 7), (1000, 3, 3, 5), (129, 4096, 256, 1),
+                                     (5000, 64, 64, 1), (2048, 192, 96, 1), (70000, 1024, 128, 1), (70000, 128, 1024, 1)])
 def test_gemm_nt_and_tn(M, N, K, Z):
     p = CudaPrims()
     A = rnd(Z, M, K, seed=1) if Z > 1 else rnd(M, K, seed=1)
@@ -42,6 +43,10 @@ def test_gemm_nt_and_tn(M, N, K, Z):
     ref_tn = torch.matmul(Bm.double().transpose(-1, -2), A.double())
     close(p.gemm_tn(Bm, A), ref_tn, 3e-6 * max(1, M ** 0.5), 'tn')
     close(p.transpose(A), A.transpose(-1, -2), 0.0, 'transpose')
+    acc = ref_tn.float().clone()
+    p.gemm_tn(Bm, A, out=acc)           # accumulate form used for the weight gradients
+    close(acc, 2 * ref_tn, 3e-6 * max(1, M ** 0.5), 'tn accumulate')
+    close(p.gemm_nt(A, W), ref - bias.double(), 2e-6 * max(1, K ** 0.5), 'nt without bias')
 
 
 def test_gemm_tn_split_reduction_large_m():
@@ -92,6 +97,25 @@ def test_maxpool_forward_backward(B, n, C):
     _, arg_t = p.maxpool_fwd(yt, B, n)
     first = (yt.view(B, n, C) == yt.view(B, n, C).max(dim=1, keepdim=True)[0]).float().argmax(dim=1)
     assert torch.equal(arg_t.long(), first)
+
+
+@pytest.mark.parametrize('B,n,C,relu', [(4, 300, 1024, True), (3, 1000, 1024, False), (6, 1300, 128, True), (2, 5, 3, True)])
+def test_fused_batchnorm_maxpool_matches_unfused(B, n, C, relu):
+    p = CudaPrims()
+    z = rnd(B * n, C, seed=30, scale=1.5) - (0.8 if relu else 0.0)
+    gamma, beta = rnd(C, seed=31) * 0.3 + 1.0, rnd(C, seed=32) * 0.2
+    gamma[::7] *= -1.0                       # negative scales: the arg-max of the output is the arg-min of z
+    y, mean, invstd = p.bn_forward(z, gamma, beta, relu)
+    out_ref, arg_ref = p.maxpool_fwd(y, B, n)
+    out, arg, mean2, invstd2 = p.bn_maxpool_forward(z, B, n, gamma, beta, relu)
+    assert torch.equal(out, out_ref) and torch.equal(arg, arg_ref)
+    assert torch.equal(mean, mean2) and torch.equal(invstd, invstd2)
+    dout = rnd(B, C, seed=33)
+    dz_ref, dg_ref, db_ref = p.bn_backward(p.maxpool_bwd(dout, arg_ref, n), z, y if relu else None, mean, invstd, gamma)
+    dz, dg, db = p.bn_maxpool_backward(dout, arg, out, z, mean, invstd, gamma, relu, B, n)
+    close(dz, dz_ref, 1e-5, 'fused dz')
+    close(dg, dg_ref, 1e-5, 'fused dgamma')
+    close(db, db_ref, 1e-5, 'fused dbeta')
 
 
 def test_loss_quaternion_and_elementwise_ops():
