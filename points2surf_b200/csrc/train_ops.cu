@@ -418,6 +418,12 @@ int sm_count() {
 void op_gemm_tn(const float* A, int64_t a_stride_z, int lda, const float* B, int64_t b_stride_z, int ldb, float* C,
                 int64_t c_stride_z, int ldc, int M, int N, int K, int batch, bool accumulate, cudaStream_t st) {
     if (N <= 0 || K <= 0 || batch <= 0) return;
+    if (batch == 1 && M > 0 && gemm_tn_tc_ok(A, lda, B, ldb, M, N, K)) {
+        // large weight gradients: split-precision tensor-core kernel (gemm_tn_tc.cu), partial tiles added atomically
+        if (!accumulate) P2S_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * K, N, st));
+        launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, M, N, K, st);
+        return;
+    }
     const int tiles = (int)(cdiv(N, kTnN) * cdiv(K, kTnK)) * batch;
     int splits = 1;
     if (M > 2048) {

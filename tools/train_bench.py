@@ -44,10 +44,11 @@ def main():
     sd = {k: t.to(dev) for k, t in synth.make_state_dict(a.model, seed=0).items()}
     batch = {k: t.to(dev) for k, t in make_train_batch(per_rank, seed=100 + rank).items()}
     ts = TrainStep(sd, v['use_point_stn'], v['shared_transformer'], lr=1e-4)
-    prof = {}
+    prof, shapes = {}, {}
     if a.profile:
         p = ts.p
-        for name in ('gemm_nt', 'gemm_tn', 'transpose', 'bn_forward', 'bn_backward', 'col_sum', 'maxpool_fwd', 'maxpool_bwd',
+        for name in ('gemm_nt', 'gemm_tn', 'transpose', 'bn_forward', 'bn_backward', 'bn_maxpool_forward', 'bn_maxpool_backward',
+                     'col_sum', 'maxpool_fwd', 'maxpool_bwd',
                      'axpy_', 'center', 'loss', 'sgd_', 'add_row_', 'quat_to_rot', 'quat_to_rot_bwd'):
             fn = getattr(p, name)
 
@@ -57,15 +58,22 @@ def main():
                     t0 = time.perf_counter()
                     out = fn(*args, **kw)
                     torch.cuda.synchronize()
+                    dt = (time.perf_counter() - t0) * 1e3
                     d = prof.setdefault(name, [0, 0.0])
                     d[0] += 1
-                    d[1] += (time.perf_counter() - t0) * 1e3
+                    d[1] += dt
+                    if name in ('gemm_nt', 'gemm_tn'):
+                        key = '%s %s x %s' % (name, tuple(args[0].shape), tuple(args[1].shape))
+                        d = shapes.setdefault(key, [0, 0.0])
+                        d[0] += 1
+                        d[1] += dt
                     return out
                 return inner
             setattr(p, name, wrap())
     for _ in range(a.warmup):
         ts.step(batch)
     prof.clear()
+    shapes.clear()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -91,6 +99,8 @@ def main():
             tot = sum(d[1] for d in prof.values())
             for name, d in sorted(prof.items(), key=lambda kv: -kv[1][1]):
                 print('  %-16s %5d calls  %9.2f ms/step  %5.1f %%' % (name, d[0] // a.steps, d[1] / a.steps, 100 * d[1] / tot))
+            for key, d in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:24]:
+                print('    %-64s %3d calls  %8.3f ms/step' % (key, d[0] // a.steps, d[1] / a.steps))
     if world > 1:
         dist.destroy_process_group()
 
