@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
     extern __shared__ __align__(1024) uint8_t smem[];
     FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int m0 = blockIdx.x * 128, nt = blockIdx.y;
+    const int m0 = blockIdx.y * 128, nt = blockIdx.x;   // N tiles of one row block are adjacent: A is re-read from L2
     const int nk = K / kBK;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 129); mbar_init(&bars->empty[s], 1); }
@@ -233,7 +233,8 @@ void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bia
     if (M <= 0) return;
     const bool padded_ok = !pack_img && N % 4 == 0 && N >= 64 && K % kBK == 0;   // partial last N tile (training GEMMs)
     P2S_CHECK((fc_tc_supported(N, K) || padded_ok) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
-    dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 128), 1);
+    P2S_CHECK(cdiv(M, 128) <= 65535, "too many rows for one launch");
+    dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, 128), 1);
     P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img);
 }
 

@@ -72,3 +72,50 @@ def test_slabs_partition_every_size():
             for (f, c), (f2, _) in zip(slabs, slabs[1:]):
                 assert f + c == f2
             assert max(c for _, c in slabs) - min(c for _, c in slabs) <= 1
+
+
+def _train_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers_train import TorchPrims, make_train_batch
+    from points2surf_b200 import synth
+    from points2surf_b200.train import TrainStep
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        sd = synth.make_state_dict('max', seed=4)
+        ts = TrainStep(sd, 0, 0, points_per_patch=16, sub_sample_size=24, device='cpu', prims=TorchPrims(), dtype=torch.float64)
+        batch = {k: t.double() for k, t in make_train_batch(4, 16, 24, seed=50 + rank).items()}
+        ts.step(batch)
+        q.put((rank, ts.flat_params.clone().numpy(), ts.flat_grads.clone().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_gloo():
+    """Two ranks, different shards: after the step both hold the same parameters, and the applied gradient is the
+    mean of the two per-rank gradients (computed again in this process without a process group)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers_train import TorchPrims, make_train_batch
+    from points2surf_b200 import synth
+    from points2surf_b200.train import TrainStep
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    local = []
+    for rank in range(2):
+        ts = TrainStep(synth.make_state_dict('max', seed=4), 0, 0, points_per_patch=16, sub_sample_size=24, device='cpu',
+                       prims=TorchPrims(), dtype=torch.float64)
+        ts.step({k: t.double() for k, t in make_train_batch(4, 16, 24, seed=50 + rank).items()})
+        local.append(ts.flat_grads.clone().numpy())
+    np.testing.assert_allclose(res[0][2], 0.5 * (local[0] + local[1]), rtol=1e-12, atol=1e-14)
