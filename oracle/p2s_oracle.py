@@ -247,14 +247,13 @@ def _pointnetfeat(sd, p, x, point_stn):
     return torch.max(x, dim=2)[0], trans
 
 
-def model_forward(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms,
+def _model_forward_impl(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms,
                   use_point_stn=True, shared_transformer=True, return_aux=False):
     """PointsToSurfModel.forward in eval mode (single_transformer=0, use_feat_stn=1, sym_op='max').
     `sd` is a reference-named state dict WITHOUT the 'module.' prefix.  Inputs are [B,P,3],
     [B,S,3], [B,3] float32 arrays/tensors; pts_sub_sample_ms is NOT modified (the reference centres
     it in place, points_to_surf_model.py:303).  Returns [B,2] float32 logits (numpy)."""
     import torch
-    torch.set_grad_enabled(False)
     as_t = lambda a: a.clone() if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
     patch = as_t(patch_pts_ps).float().transpose(1, 2)
     shape = as_t(pts_sub_sample_ms).float().transpose(1, 2)
@@ -283,6 +282,15 @@ def model_forward(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms,
     x = _fc_bn(sd, x, 'fc4', None, relu=False)
     out = x.numpy()
     return (out, aux) if return_aux else out
+
+
+def model_forward(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms,
+                  use_point_stn=True, shared_transformer=True, return_aux=False):
+    """PointsToSurfModel.forward in eval mode, without autograd (see _model_forward_impl)."""
+    import torch
+    with torch.no_grad():
+        return _model_forward_impl(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms, use_point_stn,
+                                   shared_transformer, return_aux)
 
 
 # --------------------------------------------------------------------------------------

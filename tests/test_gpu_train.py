@@ -65,8 +65,9 @@ def test_batchnorm_forward_backward(M, C, relu):
     y, mean, invstd = p.bn_forward(z, gamma, beta, relu, rm, rv)
     zt = z.double().requires_grad_(True)
     gt, bt = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
-    yr = torch.nn.functional.batch_norm(zt, rm_ref.double(), rv_ref.double(), gt, bt, training=True, momentum=0.1, eps=1e-5)
-    yr = torch.relu(yr) if relu else yr
+    with torch.enable_grad():
+        yr = torch.nn.functional.batch_norm(zt, rm_ref.double(), rv_ref.double(), gt, bt, training=True, momentum=0.1, eps=1e-5)
+        yr = torch.relu(yr) if relu else yr
     close(y, yr.detach(), 1e-5, 'bn y')
     close(rm, 0.9 * rm_ref.double() + 0.1 * z.double().mean(0), 1e-5, 'running mean')
     if M > 1:
@@ -177,35 +178,41 @@ def test_train_iteration_matches_reference_digest(variant):
 
 
 def test_train_two_steps_match_cpu_oracle_and_feed_inference():
-    # two iterations (momentum path) of 32 queries against the f64 CPU oracle, with a small learning rate so that the
-    # second iteration stays in the regime where gradient noise maps linearly to the result; then the trained
-    # state_dict drives the inference engine (the train -> eval hand-over of the reference, points_to_surf_train.py:512-517)
+    # two iterations (momentum path) of 32 queries against the f64 CPU oracle, on the `max` variant whose gradients are
+    # well conditioned in fp32 (no QSTN: 0.01 / 0.004 worst-tensor / global noise); then a vanilla model takes two steps
+    # and its state_dict drives the inference engine (the train -> eval hand-over of the reference,
+    # points_to_surf_train.py:512-517)
     from points2surf_b200 import ops
-    lr = 1e-4
-    sd = synth.make_state_dict('vanilla', seed=31)
+    lr = 1e-3
+    sd = synth.make_state_dict('max', seed=31)
     b1, b2 = make_train_batch(32, seed=5), make_train_batch(32, seed=6)
-    r1 = train_oracle.train_iteration(sd, b1, 1, 1, lr=lr, dtype=torch.float64)
+    r1 = train_oracle.train_iteration(sd, b1, 0, 0, lr=lr, dtype=torch.float64)
     sd2 = dict(sd)
     sd2.update(r1['new_state'])
-    r2 = train_oracle.train_iteration(sd2, b2, 1, 1, lr=lr, mom_bufs=r1['mom_bufs'], dtype=torch.float64)
-    ts = TrainStep({k: t.to(DEV) for k, t in sd.items()}, 1, 1, lr=lr)
+    r2 = train_oracle.train_iteration(sd2, b2, 0, 0, lr=lr, mom_bufs=r1['mom_bufs'], dtype=torch.float64)
+    ts = TrainStep({k: t.to(DEV) for k, t in sd.items()}, 0, 0, lr=lr)
     l1 = ts.step(_cuda_batch(b1))
     l2 = ts.step(_cuda_batch(b2))
-    for got, want in zip(l1, r1['losses']):          # first iteration: pure forward
-        assert abs(float(got) - want) < 1e-3 * want, (float(got), want)
-    for got, want in zip(l2, r2['losses']):          # second iteration: through the (noisy) first update
-        assert abs(float(got) - want) < 2e-2 * want, (float(got), want)
-    # total parameter movement after two steps, lr * (1.9 g1 + g2), in the L2 sense
+    for got, want in zip(list(l1) + list(l2), r1['losses'] + r2['losses']):
+        assert abs(float(got) - want) < 5e-3 * want, (float(got), want)
     new = ts.state_dict()
-    moved = {k: (new[k].cpu().double() - sd[k].double()) for k in r2['grads']}
+    moved = {k: (new[k].cpu().double() - sd[k].double()) for k in r2['grads']}       # lr * (1.9 g1 + g2)
     moved_ref = {k: (r2['new_state'][k] - sd[k].double()) for k in r2['grads']}
-    # two noisy iterations compound on the QSTN tensors (0.16 measured on point_stn.conv1.weight)
-    compare_gradients_l2(moved, moved_ref, tol_tensor=2.5e-1, tol_global=5e-2)
+    compare_gradients_l2(moved, moved_ref, tol_tensor=1e-1, tol_global=3e-2)
     assert int(new['bn2.num_batches_tracked']) == 102
-    eng = ops.Engine({k: t.cpu() for k, t in new.items()}, 1, 1, precision='fp32')
+    for name in ('bn2.running_mean', 'feat_local.bn3.running_var'):
+        r = r2['new_state'][name]
+        assert float((new[name].cpu().double() - r).abs().max()) <= 2e-3 * float(r.abs().max()) + 1e-6, name
+
+    sdv = synth.make_state_dict('vanilla', seed=32)
+    tv = TrainStep({k: t.to(DEV) for k, t in sdv.items()}, 1, 1, lr=1e-4)
+    tv.step(_cuda_batch(b1))
+    lv = tv.step(_cuda_batch(b2))
+    assert all(np.isfinite(float(l)) for l in lv)
+    eng = ops.Engine({k: t.cpu() for k, t in tv.state_dict().items()}, 1, 1, precision='fp32')
     inp = synth.make_model_inputs(4, seed=9)
     out = eng.forward(*(torch.from_numpy(inp[k]).to(DEV) for k in ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms')))
     assert torch.isfinite(out).all()
     with pytest.raises(ValueError):
-        ts.forward({'patch_pts_ps': torch.zeros(2, 10, 3, device=DEV), 'pts_sub_sample_ms': torch.zeros(2, 1000, 3, device=DEV),
+        tv.forward({'patch_pts_ps': torch.zeros(2, 10, 3, device=DEV), 'pts_sub_sample_ms': torch.zeros(2, 1000, 3, device=DEV),
                     'imp_surf_query_point_ms': torch.zeros(2, 3, device=DEV)})
