@@ -391,3 +391,32 @@ def test_split_precision_tensor_core_path_matches_fp32(variant):
     r2 = make_engine(sd2, variant, precision='fp32').forward(*a2).cpu().numpy()
     o2 = make_engine(sd2, variant, precision='tc', guard_band=1e9).forward(*a2).cpu().numpy()
     assert np.abs(o2 - r2).max() < 2e-3
+
+
+# ------------------------------------------------------------------ section 8f-2: other patch / sub-sample sizes
+# (small_kNN: 75-point patches; ragged tile tails on every path: 75, 200, 511 are no multiples of the 128-point tile)
+@pytest.mark.parametrize('variant,P,S', [('uniform', 75, 1000), ('vanilla', 200, 500), ('max', 511, 300)])
+def test_other_patch_and_subsample_sizes(variant, P, S):
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict(variant, seed=77)
+    inp = synth.make_model_inputs(24, points_per_patch=P, sub_sample_size=S, seed=78)
+    ref = orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'],
+                            v['use_point_stn'], v['shared_transformer'])
+    args = (cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms']))
+    scale = max(1.0, np.abs(ref).max())
+    e32 = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=P, sub_sample_size=S, precision='fp32')
+    assert np.abs(e32.forward(*args).cpu().numpy() - ref).max() < 2e-3 * scale
+    etc = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=P, sub_sample_size=S, precision='tc',
+                     guard_band=0.0)
+    assert np.abs(etc.forward(*args).cpu().numpy() - ref).max() < 3e-2 * scale
+    etc.set_precision('tc', guard_band=1e9)            # every query through the split-precision recompute path
+    assert np.abs(etc.forward(*args).cpu().numpy() - ref).max() < 2e-3 * scale
+    # the assembly kernels at the same sizes: exact kNN order and radius against the brute-force oracle
+    cloud = synth.make_cloud('torus', 2500, seed=79)
+    q = cloud[:40] + 0.01
+    ids, patch, radius = ops.knn_patch(cu(cloud), cu(q.astype(np.float32)), P)
+    for i in range(0, 40, 7):
+        rid = orc.knn_bruteforce(cloud, q[i].astype(np.float32), P)
+        assert np.array_equal(ids[i].cpu().numpy(), np.asarray(rid[0] if isinstance(rid, tuple) else rid).astype(np.int32))
+    with pytest.raises(ops.P2SError):
+        ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=1200, sub_sample_size=S)   # large_kNN: documented limit 512
