@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--points', type=int, default=10000)
     ap.add_argument('--precision', default='auto', choices=['auto', 'tc', 'fp32'])
     ap.add_argument('--guard_band', type=float, default=None)
+    ap.add_argument('--mix_shapes', action='store_true', help='sphere / torus / box per rank instead of same-size spheres')
     ap.add_argument('--cpu_sample', type=int, default=256, help='queries in the bounded CPU-baseline sample')
     ap.add_argument('--seed', type=int, default=40938661)
     return ap.parse_args()
@@ -56,8 +57,10 @@ def dist_env():
 
 def make_workload(args, rank):
     from points2surf_b200 import synth
-    kinds = ['sphere', 'torus', 'box']
-    cloud = synth.make_cloud(kinds[rank % 3], args.points, seed=rank)
+    # weak scaling: every rank reconstructs a shape of the same kind and size (sphere, different seed), so the per-GPU
+    # work is fixed as N grows; --mix_shapes gives the sphere / torus / box mix of SURVEY config 3 (unequal Q per rank)
+    kinds = ['sphere', 'torus', 'box'] if args.mix_shapes else ['sphere']
+    cloud = synth.make_cloud(kinds[rank % len(kinds)], args.points, seed=rank)
     sd = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4)
     return cloud, sd
 
@@ -65,14 +68,31 @@ def make_workload(args, rank):
 # ----------------------------------------------------------------------------------------------------
 # CPU side: oracle port of the reference path (test infrastructure used as the timed CPU baseline)
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None):
-    """queries/s of the reference algorithm on the host cores for `n_queries` queries of this workload."""
+_ASM = {}
+
+
+def _assemble_chunk(job):
+    """Worker of the assembly pool (the reference runs PointcloudPatchDataset.__getitem__ in DataLoader worker processes,
+    source/points_to_surf_eval.py:141-147)."""
+    from oracle import p2s_oracle as orc
+    idx, seed = job
+    g = _ASM
+    rng = np.random.RandomState(seed)
+    return [orc.assemble_query(g['cloud'], g['kd'], g['qpts'][i], 300, 1000, rng, g['uniform']) for i in idx]
+
+
+def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None, threads=None, workers=None):
+    """queries/s of the reference algorithm on the host cores for `n_queries` queries of this workload: per-query assembly
+    in `workers` processes (like the reference's DataLoader workers), network with `threads` torch threads."""
+    import multiprocessing as mp
     import torch
     from oracle import p2s_oracle as orc
     from points2surf_b200 import synth
     v = synth.VARIANTS[args.model]
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = threads or cores
+    workers = workers if workers is not None else max(1, min(cores - 1, 32))
+    torch.set_num_threads(threads)
     if fc4_bias is not None:
         sd = dict(sd)
         sd['fc4.bias'] = torch.from_numpy(np.asarray(fc4_bias, dtype=np.float32))
@@ -82,9 +102,18 @@ def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None):
     Q = len(qpts)
     sel = np.linspace(0, Q - 1, n_queries).astype(np.int64)
     kd = orc.make_kdtree(cloud)
-    rng = np.random.RandomState(args.seed)
+    _ASM.update(cloud=cloud, kd=kd, qpts=qpts, uniform=bool(v['uniform_subsample']))
     t0 = time.perf_counter()
-    items = [orc.assemble_query(cloud, kd, qpts[i], 300, 1000, rng, bool(v['uniform_subsample'])) for i in sel]
+    if workers > 1 and n_queries >= 2 * workers:
+        jobs = [(c, args.seed + j) for j, c in enumerate(np.array_split(sel, workers))]
+        try:
+            with mp.get_context('fork').Pool(workers) as pool:   # fork: the cloud / kd-tree are inherited, not pickled
+                items = [it for part in pool.map_async(_assemble_chunk, jobs).get(timeout=180) for it in part]
+        except Exception:                                        # a stuck or failed pool must not cost the bench line
+            workers = 1
+            items = _assemble_chunk((sel, args.seed))
+    else:
+        items = _assemble_chunk((sel, args.seed))
     patch = np.stack([it['patch_pts_ps'] for it in items])
     sub = np.stack([it['pts_sub_sample_ms'] for it in items])
     rad = np.array([it['patch_radius_ms'] for it in items])
@@ -95,8 +124,19 @@ def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None):
     t_net = time.perf_counter() - t0
     # candidate grid is a per-shape cost: charge the sample its share
     total = t_asm + t_net + t_grid * (n_queries / max(Q, 1))
-    return dict(value=n_queries / total, cores=cores, Q=Q, t_assemble_s=t_asm, t_network_s=t_net,
-                t_grid_s=t_grid, sdf_checksum=float(np.abs(sdf).sum()))
+    return dict(value=n_queries / total, cores=max(threads, workers), threads=threads, workers=workers, Q=Q, t_assemble_s=t_asm,
+                t_network_s=t_net, t_grid_s=t_grid, sdf_checksum=float(np.abs(sdf).sum()))
+
+
+def best_cpu_threads(args, cloud, sd):
+    """Give the CPU arm its best configuration: probe the torch thread count on a 32-query sample."""
+    cores = os.cpu_count() or 1
+    best, best_rate = cores, 0.0
+    for t in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+        r = cpu_reference_rate(args, cloud, sd, 32, threads=t)
+        if r['value'] > best_rate:
+            best, best_rate = t, r['value']
+    return best, best_rate
 
 
 def run_reference(args):
@@ -104,10 +144,14 @@ def run_reference(args):
     if rank != 0:
         return
     cloud, sd = make_workload(args, 0)
+    # bounded sample per step: size it from a 32-query probe so that the whole --warmup/--steps run ends in ~3 minutes
+    threads, probe_rate = best_cpu_threads(args, cloud, sd)
+    budget_s = 150.0
+    args.cpu_sample = int(max(16, min(args.cpu_sample, probe_rate * budget_s / max(1, args.warmup + args.steps))))
     rates = []
     r = None
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_rate(args, cloud, sd, args.cpu_sample)
+        r = cpu_reference_rate(args, cloud, sd, args.cpu_sample, threads=threads)
         if i >= args.warmup:
             rates.append(r['value'])
     value = float(np.mean(rates))
@@ -118,16 +162,17 @@ def run_reference(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, r['Q']),
         'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': r['cores'], 'kind': 'port',
-                         'sample': '%d queries evenly spaced over the %d-query band per step (oracle port: scipy cKDTree kNN, '
-                                   'NumPy RandomState sub-sample, torch-CPU fp32 network)' % (args.cpu_sample, r['Q'])},
+                         'sample': '%d queries evenly spaced over the %d-query band per step (oracle port: scipy cKDTree kNN + '
+                                   'NumPy RandomState sub-sample in %d worker processes, torch-CPU fp32 network on %d threads)'
+                                   % (args.cpu_sample, r['Q'], r['workers'], r['threads'])},
         'e2e': {'value': value, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
 
 
 def workload_config(args, Q):
-    return {'workload': '%s model, 1 synthetic %d-pt cloud per GPU, grid_res=%d, epsilon=%d, kNN 300 + 1000-pt sub-sample'
-                        % (args.model, args.points, args.grid_res, args.epsilon),
+    return {'workload': '%s model, 1 synthetic %d-pt %s cloud per GPU, grid_res=%d, epsilon=%d, kNN 300 + 1000-pt sub-sample'
+                        % (args.model, args.points, 'sphere/torus/box' if args.mix_shapes else 'sphere', args.grid_res, args.epsilon),
             'queries_per_shape': int(Q), 'l2': 'flushed between timed iterations (256 MiB write)'}
 
 
@@ -315,8 +360,11 @@ def run_b200(args):
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
                         'flops_per_launch': prof['flops'] / prof['launches'], 'ms_per_launch': prof['ms'] / prof['launches'],
                         'share_of_step': prof['ms'] / dev_ms}
-        cpu = cpu_reference_rate(args, cloud, sd, args.cpu_sample, fc4_bias=fc4_bias) if args.cpu_sample > 0 else \
-            dict(value=None, cores=os.cpu_count(), t_assemble_s=0.0, t_network_s=0.0)
+        if args.cpu_sample > 0 and world == 1:
+            cpu_threads, _ = best_cpu_threads(args, cloud, sd)
+            cpu = cpu_reference_rate(args, cloud, sd, args.cpu_sample, fc4_bias=fc4_bias, threads=cpu_threads)
+        else:
+            cpu = dict(value=None, cores=os.cpu_count(), threads=0, workers=0, t_assemble_s=0.0, t_network_s=0.0)
         line = {
             'metric': 'SDF queries/sec at grid_res=%d' % args.grid_res, 'value': value, 'unit': 'queries/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
@@ -329,8 +377,8 @@ def run_b200(args):
             'clocks': sampler.summary(),
             'roofline': roofline,
             'cpu_baseline': {'value': cpu['value'], 'unit': 'queries/s', 'cores': cpu['cores'], 'kind': 'port',
-                             'sample': '%d queries evenly spaced over the band (assemble %.2fs, network %.2fs)'
-                                       % (args.cpu_sample, cpu['t_assemble_s'], cpu['t_network_s'])},
+                             'sample': '%d queries evenly spaced over the band (assembly in %d worker processes %.2fs, network on %d torch threads %.2fs)'
+                                       % (args.cpu_sample, cpu['workers'], cpu['t_assemble_s'], cpu['threads'], cpu['t_network_s'])},
             'tensor_flops_per_s': value * FLOP_PER_QUERY[args.model],
             'mesh_stage': mesh_stage,
         }

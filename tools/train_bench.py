@@ -30,6 +30,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=2)
     ap.add_argument('--model', default='vanilla')
+    ap.add_argument('--cpu_sample', type=int, default=0, help='queries of one CPU-oracle iteration timed beside it (0 = skip)')
     ap.add_argument('--profile', action='store_true', help='per-primitive time table (synchronising; slower)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -94,6 +95,17 @@ def main():
                'tflops_algorithmic': 3 * FLOP_FWD[a.model] * a.batch / (ms * 1e-3) / 1e12,
                'launches_per_step': ops.launch_count() / a.steps, 'loss': [float(l) for l in losses],
                'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9}
+        if a.cpu_sample > 0 and world == 1:
+            from oracle import train_oracle
+            torch.set_num_threads(os.cpu_count() or 1)
+            cb = make_train_batch(a.cpu_sample, seed=100)
+            csd = synth.make_state_dict(a.model, seed=0)
+            train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])   # warm-up
+            t0 = time.perf_counter()
+            train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])
+            dt = time.perf_counter() - t0
+            out['cpu_baseline'] = {'value': a.cpu_sample / dt, 'unit': 'queries/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                   'sample': 'one training iteration of %d queries with the oracle port (torch CPU autograd)' % a.cpu_sample}
         print(json.dumps(out))
         if prof:
             tot = sum(d[1] for d in prof.values())
