@@ -136,6 +136,123 @@ __global__ void apply_vote_kernel(int8_t* __restrict__ S, const uint8_t* __restr
     if (v == 0) atomicAdd(&c->iters, 1);
 }
 
+// ---- word-wide variants (res % 4 == 0): one thread = 4 consecutive z voxels packed in a 32-bit word, per-byte SIMD adds
+// (sums stay within int8: |S| <= 1, three axes of at most 11 taps each only when sigma <= 5: 5^3 = 125; larger sigma use
+// the scalar kernels), grid-stride loops and ONE counter atomic per block -- the scalar kernels above issue one
+// same-address atomic per warp (res^3 / 32 of them), which serialises to ~0.25 ms per kernel at 256^3.
+__device__ __forceinline__ void block_count_add_once(unsigned v, unsigned long long* dst) {
+    __shared__ unsigned warp_sum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned t = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0 && t) atomicAdd(dst, (unsigned long long)t);
+    }
+}
+
+template <int AXIS>   // 2: z (inside the word and its neighbours), 1: y
+__global__ void __launch_bounds__(256)
+box_axis4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int res, int lo, int hi, Ctrl* c, int iter) {
+    if (c->done) return;
+    if (AXIS == 2 && c->cnt[iter & 1] == 0) {  // `if unknown_before.sum() == 0: break`  (sdf.py:157-159)
+        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
+        return;
+    }
+    if (AXIS == 2 && blockIdx.x == 0 && threadIdx.x == 0) { c->cntN = 0; c->cnt[(iter + 1) & 1] = 0; }
+    const unsigned rw = (unsigned)res >> 2;
+    const unsigned W = (unsigned)res * (unsigned)res * rw;
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+        const unsigned wz = w % rw, row = w / rw;
+        if (AXIS == 2) {
+            const uint32_t* r = in + (size_t)row * rw;
+            // bytes b[8 + j] = position 4*wz + j, j in [-8, 11], replicated at the row ends
+            int b[20];
+            const int dmin = lo < -4 ? -2 : (lo < 0 ? -1 : 0), dmax = hi > 4 ? 2 : (hi > 0 ? 1 : 0);
+            const uint32_t first = r[0] & 0xffu, last = r[rw - 1] >> 24;
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                uint32_t x = 0;
+                if (d >= dmin && d <= dmax) {
+                    const int wi = (int)wz + d;
+                    x = wi < 0 ? first * 0x01010101u : (wi >= (int)rw ? last * 0x01010101u : r[wi]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[4 * (d + 2) + i] = (int)(int8_t)(x >> (8 * i));
+            }
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int acc = 0;
+#pragma unroll
+                for (int t = -5; t <= 5; ++t)           // static indices: b[] stays in registers
+                    if (t >= lo && t <= hi) acc += b[8 + k + t];
+                o |= ((uint32_t)acc & 0xffu) << (8 * k);
+            }
+            out[w] = o;
+        } else {
+            const unsigned iy = row % (unsigned)res, ix = row / (unsigned)res;
+            uint32_t acc = 0;
+            for (int t = lo; t <= hi; ++t) {
+                const int p = min(max((int)iy + t, 0), res - 1);
+                acc = __vadd4(acc, in[((size_t)ix * res + p) * rw + wz]);
+            }
+            out[w] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+box_x_vote4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ vote, int res, int lo, int hi, float thr, Ctrl* c) {
+    if (c->done) return;
+    const unsigned rw = (unsigned)res >> 2;
+    const unsigned plane = (unsigned)res * rw;         // words per x plane
+    const unsigned W = (unsigned)res * plane;
+    unsigned z = 0;
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+        const unsigned ix = w / plane, rem = w - ix * plane;
+        uint32_t acc = 0;
+        for (int t = lo; t <= hi; ++t) {
+            const int p = min(max((int)ix + t, 0), res - 1);
+            acc = __vadd4(acc, in[(size_t)p * plane + rem]);
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = (int)(int8_t)(acc >> (8 * k));
+            int s = 0;
+            if (!(fabsf((float)a) < thr)) s = a > 0 ? 1 : (a < 0 ? -1 : 0);
+            o |= ((uint32_t)s & 0xffu) << (8 * k);
+            z += (s == 0);
+        }
+        vote[w] = o;
+    }
+    block_count_add_once(z, &c->cntN);
+}
+
+__global__ void __launch_bounds__(256)
+apply_vote4_kernel(uint32_t* __restrict__ S, const uint32_t* __restrict__ U0, const uint32_t* __restrict__ vote, unsigned W,
+                   Ctrl* c, int iter) {
+    if (c->done) return;
+    if (c->cntN >= c->cnt[iter & 1]) {       // `if unknown_after.sum() >= unknown_before.sum(): break`
+        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
+        return;
+    }
+    unsigned z = 0;
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+        const uint32_t m = __vcmpne4(U0[w], 0u);          // 0xff where the voxel was unknown at the start
+        const uint32_t s = S[w];
+        const uint32_t n = (vote[w] & m) | (s & ~m);
+        if (n != s) S[w] = n;
+        z += (unsigned)__popc(__vcmpeq4(n, 0u)) >> 3;
+    }
+    block_count_add_once(z, &c->cnt[(iter + 1) & 1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->iters, 1);
+}
+
 // vol[vol == 0] = S[vol == 0]; clamp to [-1, 1]   (sdf.py:179,200-202)
 __global__ void finalize_kernel(float* __restrict__ vol, const int8_t* __restrict__ S, int64_t V) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,11 +296,25 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     P2S_LAUNCH(init_sign_kernel, blocks, 256, 0, st, vol, res, S, U0, ctrl);
     // convolve(ones(sigma^3), mode='nearest'): output o sums inputs o-ceil(s/2)+1 .. o+floor(s/2)
     const int lo = -((sigma + 1) / 2) + 1, hi = sigma / 2;
+    // word-wide kernels: 4 z voxels per thread, needs word-aligned rows and box sums that fit int8 (sigma^3 <= 127)
+    const bool words = (res % 4 == 0) && sigma <= 5;
+    int dev_id = 0, sms = 148;
+    P2S_CUDA(cudaGetDevice(&dev_id));
+    P2S_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+    const unsigned wblocks = (unsigned)std::min<int64_t>(cdiv(V / 4, 256), (int64_t)sms * 8);
     Ctrl h{};
     int iter = 0;
     const int kBatch = 8;
     for (;;) {
         for (int b = 0; b < kBatch; ++b, ++iter) {
+            if (words) {
+                P2S_LAUNCH(box_axis4_kernel<2>, wblocks, 256, 0, st, (const uint32_t*)S, (uint32_t*)t1, res, lo, hi, ctrl, iter);
+                P2S_LAUNCH(box_axis4_kernel<1>, wblocks, 256, 0, st, (const uint32_t*)t1, (uint32_t*)t2, res, lo, hi, ctrl, iter);
+                P2S_LAUNCH(box_x_vote4_kernel, wblocks, 256, 0, st, (const uint32_t*)t2, (uint32_t*)vote, res, lo, hi, thr, ctrl);
+                P2S_LAUNCH(apply_vote4_kernel, wblocks, 256, 0, st, (uint32_t*)S, (const uint32_t*)U0, (const uint32_t*)vote,
+                           (unsigned)(V / 4), ctrl, iter);
+                continue;
+            }
             P2S_LAUNCH(box_axis_kernel<2>, blocks, 256, 0, st, S, t1, res, lo, hi, ctrl, iter);
             P2S_LAUNCH(box_axis_kernel<1>, blocks, 256, 0, st, t1, t2, res, lo, hi, ctrl, iter);
             P2S_LAUNCH(box_x_vote_kernel, blocks, 256, 0, st, t2, vote, res, lo, hi, thr, ctrl);

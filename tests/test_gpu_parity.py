@@ -194,7 +194,8 @@ def test_sign_propagation_golden(name):
     assert np.array_equal(vol2.cpu().numpy(), np.clip(g[name + '_vol_s3t5'], -1.0, 1.0))
 
 
-@pytest.mark.parametrize('res,sigma,thr', [(24, 5, 13), (33, 4, 9), (48, 5, 26), (20, 2, 3)])
+# res % 4 == 0 and sigma <= 5 take the word-wide kernels, the rest the scalar ones
+@pytest.mark.parametrize('res,sigma,thr', [(24, 5, 13), (33, 4, 9), (48, 5, 26), (20, 2, 3), (36, 4, 9), (44, 7, 40), (64, 1, 1), (52, 3, 5)])
 def test_sign_propagation_vs_oracle(res, sigma, thr):
     cloud = synth.make_cloud('torus', 4000, seed=9)
     qpts = orc.query_grid(cloud, res, 3)
