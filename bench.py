@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--points', type=int, default=10000)
     ap.add_argument('--precision', default='auto', choices=['auto', 'tc', 'fp32'])
     ap.add_argument('--guard_band', type=float, default=None)
+    ap.add_argument('--skip_mesh_stage', action='store_true', help='do not run the volume / marching-cubes stage (for kernel launch lists of the queries/s step)')
     ap.add_argument('--mix_shapes', action='store_true', help='sphere / torus / box per rank instead of same-size spheres')
     ap.add_argument('--cpu_sample', type=int, default=256, help='queries in the bounded CPU-baseline sample')
     ap.add_argument('--seed', type=int, default=40938661)
@@ -291,7 +292,7 @@ def run_b200(args):
     # second half of the metric ("shapes/sec reconstructed"): SDF band -> volume -> sign propagation -> marching cubes,
     # measured on this rank's shape outside the queries/s region (HBM/L2-bound byte kernels)
     mesh_stage = None
-    if True:
+    if not args.skip_mesh_stage:
         from points2surf_b200 import sharding
         lin, sdf = step_dev()
         res = args.grid_res

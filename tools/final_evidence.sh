@@ -15,7 +15,7 @@ timeout 300 python tools/train_bench.py --batch 1024 --steps 5 --warmup 2 --cpu_
 timeout 200 python tools/train_bench.py --batch 128 --steps 5 --warmup 2 > $o/${tag}_train_b128.txt 2>&1; tail -n 1 $o/${tag}_train_b128.txt | cut -c1-300
 # ncu: launch list of one bench step (times only: 1 pass per kernel)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file $o/${tag}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --cpu_sample 0 > $o/${tag}_launches.log 2>&1
+    python bench.py --steps 1 --warmup 3 --cpu_sample 0 --skip_mesh_stage > $o/${tag}_launches.log 2>&1
 python tools/summarize_launches.py $o/${tag}_launches.csv > $o/${tag}_launches_summary.txt 2>&1; head -n 14 $o/${tag}_launches_summary.txt
 # ncu --set full on the pass kernel (5 consecutive launches = one batch), source-level
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pointnet_pass -s 10 -c 5 -o $o/${tag}_pass_full \

@@ -97,15 +97,19 @@ def main():
                'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9}
         if a.cpu_sample > 0 and world == 1:
             from oracle import train_oracle
-            torch.set_num_threads(os.cpu_count() or 1)
             cb = make_train_batch(a.cpu_sample, seed=100)
             csd = synth.make_state_dict(a.model, seed=0)
-            train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])   # warm-up
-            t0 = time.perf_counter()
-            train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])
-            dt = time.perf_counter() - t0
-            out['cpu_baseline'] = {'value': a.cpu_sample / dt, 'unit': 'queries/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                   'sample': 'one training iteration of %d queries with the oracle port (torch CPU autograd)' % a.cpu_sample}
+            best = (0.0, 0)
+            for th in sorted({min(os.cpu_count() or 1, c) for c in (16, 32, os.cpu_count() or 1)}):   # give the CPU arm its best thread count
+                torch.set_num_threads(th)
+                train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])   # warm-up
+                t0 = time.perf_counter()
+                train_oracle.train_iteration(csd, cb, v['use_point_stn'], v['shared_transformer'])
+                rate = a.cpu_sample / (time.perf_counter() - t0)
+                if rate > best[0]:
+                    best = (rate, th)
+            out['cpu_baseline'] = {'value': best[0], 'unit': 'queries/s', 'cores': best[1], 'kind': 'port',
+                                   'sample': 'one training iteration of %d queries with the oracle port (torch CPU autograd, best of 16 / 32 / all threads)' % a.cpu_sample}
         print(json.dumps(out))
         if prof:
             tot = sum(d[1] for d in prof.values())
