@@ -43,11 +43,20 @@ __global__ void any_nonzero_kernel(const float* __restrict__ sdf, int64_t Q, Ctr
     if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&c->nonzero_seen, 1u);
 }
 
+// block-wide sum of v, ONE atomic per block (a same-address atomic per warp serialises: res^3 / 32 of them cost
+// ~0.25 ms per kernel at 256^3).  Every thread of the block must call it.
 __device__ __forceinline__ void block_count_add(unsigned v, unsigned long long* dst) {
-    // v in {0,1,...}: warp reduce then one atomic per warp
+    __shared__ unsigned warp_sum[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned t = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0 && t) atomicAdd(dst, (unsigned long long)t);
+    }
 }
 
 // S = sign(vol), U0 = (S == 0), then the six border faces of vol (not of S) are set to -1  (sdf.py:144-154)
@@ -138,22 +147,7 @@ __global__ void apply_vote_kernel(int8_t* __restrict__ S, const uint8_t* __restr
 
 // ---- word-wide variants (res % 4 == 0): one thread = 4 consecutive z voxels packed in a 32-bit word, per-byte SIMD adds
 // (sums stay within int8: |S| <= 1, three axes of at most 11 taps each only when sigma <= 5: 5^3 = 125; larger sigma use
-// the scalar kernels), grid-stride loops and ONE counter atomic per block -- the scalar kernels above issue one
-// same-address atomic per warp (res^3 / 32 of them), which serialises to ~0.25 ms per kernel at 256^3.
-__device__ __forceinline__ void block_count_add_once(unsigned v, unsigned long long* dst) {
-    __shared__ unsigned warp_sum[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned t = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0 && t) atomicAdd(dst, (unsigned long long)t);
-    }
-}
-
+// the scalar kernels) and grid-stride loops (a few thousand counter atomics per kernel instead of one per 256 voxels).
 template <int AXIS>   // 2: z (inside the word and its neighbours), 1: y
 __global__ void __launch_bounds__(256)
 box_axis4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int res, int lo, int hi, Ctrl* c, int iter) {
@@ -230,7 +224,7 @@ box_x_vote4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ vote,
         }
         vote[w] = o;
     }
-    block_count_add_once(z, &c->cntN);
+    block_count_add(z, &c->cntN);
 }
 
 __global__ void __launch_bounds__(256)
@@ -249,7 +243,7 @@ apply_vote4_kernel(uint32_t* __restrict__ S, const uint32_t* __restrict__ U0, co
         if (n != s) S[w] = n;
         z += (unsigned)__popc(__vcmpeq4(n, 0u)) >> 3;
     }
-    block_count_add_once(z, &c->cnt[(iter + 1) & 1]);
+    block_count_add(z, &c->cnt[(iter + 1) & 1]);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->iters, 1);
 }
 
