@@ -256,7 +256,7 @@ bool gemm_nt_tc_ok(const float* A, int lda, const float* C, int ldc, int64_t M, 
         const char* e = getenv("P2S_TRAIN_GEMM_FP32");
         disabled = (e && e[0] == '1') ? 1 : 0;
     }
-    return !disabled && N % 4 == 0 && N >= 64 && K % kBK == 0 && K >= kBK && N <= 4096 && M >= 512 && M < (int64_t)1 << 31 && lda % 4 == 0 && ldc % 4 == 0 &&
+    return !disabled && N % 4 == 0 && N >= 64 && K % kBK == 0 && K >= kBK && N <= 4096 && M >= 128 && M < (int64_t)1 << 31 && lda % 4 == 0 && ldc % 4 == 0 &&
            ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
 }
 

@@ -279,18 +279,81 @@ class TrainStep:
         self.p.sgd_(self.flat_params, self.flat_grads, self.flat_mom, self.lr, self.momentum, self.steps_done == 0)
         self.steps_done += 1
 
-    def step(self, batch):
-        """One iteration of the reference's inner loop (points_to_surf_train.py:441-461): zero_grad, forward,
-        compute_loss, backward, SGD.  Returns [loss_magnitude, loss_sign] (0-d float64 tensors on the device)."""
+    def _forward_backward(self, batch):
         self.zero_grad()
         logits = self.forward(batch)
         losses, dlogits = compute_loss(logits, batch, self.outputs, self.loss_weights, self.fixed_radius, prims=self.p,
                                        need_grad=True)
         self.backward(dlogits)
+        return logits, losses
+
+    def _reduce_gradients(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat_grads)
             self.flat_grads /= dist.get_world_size()
+
+    def step(self, batch):
+        """One iteration of the reference's inner loop (points_to_surf_train.py:441-461): zero_grad, forward,
+        compute_loss, backward, SGD.  Returns [loss_magnitude, loss_sign] (0-d float64 tensors on the device)."""
+        if self._graph is not None:
+            return self._step_graph(batch)
+        logits, losses = self._forward_backward(batch)
+        self._reduce_gradients()
         self.optimizer_step()
+        self.last_logits = logits
+        return losses
+
+    # ------------------------------------------------------------------------------------------ CUDA-graph replay
+    _graph = None
+    _BATCH_KEYS = ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms', 'patch_radius_ms',
+                   'imp_surf_magnitude_ms', 'imp_surf_dist_sign_ms')
+
+    def capture_graph(self, example_batch):
+        """Capture forward+backward and the SGD update of one batch shape into two CUDA graphs (the gradient all_reduce
+        runs eagerly between them).  A step is ~400 small launches issued from Python; at the 128-queries-per-rank size
+        of BASELINE config 4 the host is the bottleneck, replaying a graph removes it.  The parameters, momentum buffers
+        and running statistics are restored after the warm-up iterations that size the scratch buffers, so capturing
+        does not train."""
+        if self.device.type != 'cuda':
+            raise ValueError('CUDA graphs need a CUDA device')
+        static = {k: example_batch[k].detach().clone().contiguous() for k in self._BATCH_KEYS}
+        saved = (self.flat_params.clone(), self.flat_mom.clone(), {k: v.clone() for k, v in self.buffers.items()}, self.steps_done)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._forward_backward(static)
+                self.optimizer_step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.flat_params.copy_(saved[0])
+        self.flat_mom.copy_(saved[1])
+        for k, v in saved[2].items():
+            self.buffers[k].copy_(v)
+        self.steps_done = saved[3]
+        bn_before = {k: int(v) for k, v in self.buffers.items() if k.endswith('num_batches_tracked')}
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            logits, losses = self._forward_backward(static)
+        with torch.cuda.graph(g2):
+            # momentum buffers are zero before the first step, so `buf = mu * buf + g` equals torch's `buf = g`
+            self.p.sgd_(self.flat_params, self.flat_grads, self.flat_mom, self.lr, self.momentum, False)
+        for k, n in bn_before.items():      # the capture pass incremented the host-side counters once: undo
+            self.buffers[k].fill_(n)
+        self._graph = (g1, g2, static, logits, losses)
+        return self
+
+    def _step_graph(self, batch):
+        g1, g2, static, logits, losses = self._graph
+        for k in self._BATCH_KEYS:
+            static[k].copy_(batch[k], non_blocking=True)
+        g1.replay()
+        self._reduce_gradients()
+        g2.replay()
+        self.steps_done += 1
+        for k, v in self.buffers.items():
+            if k.endswith('num_batches_tracked'):
+                v += 1
         self.last_logits = logits
         return losses
 

@@ -31,6 +31,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=2)
     ap.add_argument('--model', default='vanilla')
     ap.add_argument('--cpu_sample', type=int, default=0, help='queries of one CPU-oracle iteration timed beside it (0 = skip)')
+    ap.add_argument('--graph', action='store_true', help='replay the step as CUDA graphs (TrainStep.capture_graph)')
     ap.add_argument('--profile', action='store_true', help='per-primitive time table (synchronising; slower)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -45,6 +46,8 @@ def main():
     sd = {k: t.to(dev) for k, t in synth.make_state_dict(a.model, seed=0).items()}
     batch = {k: t.to(dev) for k, t in make_train_batch(per_rank, seed=100 + rank).items()}
     ts = TrainStep(sd, v['use_point_stn'], v['shared_transformer'], lr=1e-4)
+    if a.graph:
+        ts.capture_graph(batch)
     prof, shapes = {}, {}
     if a.profile:
         p = ts.p
@@ -93,7 +96,7 @@ def main():
         out = {'workload': '%s training step, global batch %d (%d per rank), P 300, S 1000, fp32' % (a.model, a.batch, per_rank),
                'n_gpus': world, 'ms_per_step': ms, 'steps_per_s': 1e3 / ms, 'queries_per_s': a.batch * 1e3 / ms,
                'tflops_algorithmic': 3 * FLOP_FWD[a.model] * a.batch / (ms * 1e-3) / 1e12,
-               'launches_per_step': ops.launch_count() / a.steps, 'loss': [float(l) for l in losses],
+               'launches_per_step': ops.launch_count() / a.steps, 'cuda_graph': bool(a.graph), 'loss': [float(l) for l in losses],
                'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9}
         if a.cpu_sample > 0 and world == 1:
             from oracle import train_oracle
