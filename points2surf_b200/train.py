@@ -100,7 +100,9 @@ class TrainStep:
                 for b in ('running_mean', 'running_var'):
                     self.buffers[name + '.' + b] = sd[name + '.' + b].to(self.device, dtype).clone().contiguous()
                 nb = sd.get(name + '.num_batches_tracked')
-                self.buffers[name + '.num_batches_tracked'] = (nb.clone() if nb is not None else torch.zeros((), dtype=torch.long))
+                # host-side counter (never read by a kernel); kept on the CPU so that it is not captured into CUDA graphs
+                self.buffers[name + '.num_batches_tracked'] = (nb.detach().cpu().clone() if nb is not None
+                                                               else torch.zeros((), dtype=torch.long))
         self.steps_done = 0
         self._eye64 = torch.eye(64, dtype=dtype, device=self.device).reshape(-1).contiguous()
 
