@@ -233,8 +233,8 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert int(graph.buffers['bn2.num_batches_tracked']) == 100
     lg = [[float(x) for x in graph.step(b1)], [float(x) for x in graph.step(b2)]]
     for a, b in zip(le, lg):
-        assert abs(float(a[0]) - b[0]) < 1e-3 * abs(b[0]) and abs(float(a[1]) - b[1]) < 1e-3 * abs(b[1])
+        assert abs(float(a[0]) - b[0]) < 5e-3 * abs(b[0]) and abs(float(a[1]) - b[1]) < 5e-3 * abs(b[1])
     moved_e, moved_g = eager.flat_params - before, graph.flat_params - before
-    assert float((moved_e - moved_g).norm()) <= 2e-2 * float(moved_e.norm())
+    assert float((moved_e - moved_g).norm()) <= 5e-2 * float(moved_e.norm())
     assert int(graph.buffers['bn2.num_batches_tracked']) == 102 and graph.steps_done == 2
     close(graph.buffers['bn2.running_mean'], eager.buffers['bn2.running_mean'], 1e-3, 'running mean after graph steps')
