@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
+from . import samplers
 from . import sdf as p2s_sdf
 from .weights import strip_module_prefix
 
@@ -41,7 +42,7 @@ def parse_arguments(args=None):
     parser.add_argument('--gpu_idx', type=int, default=0, help='CUDA device index (there is no CPU path)')
     parser.add_argument('--sparse_patches', type=int, default=False, help='unused (kept for CLI compatibility)')
     parser.add_argument('--sampling', type=str, default='full', help='only "full" is supported')
-    parser.add_argument('--patches_per_shape', type=int, default=1000, help='unused with --sampling full')
+    parser.add_argument('--patches_per_shape', type=int, default=1000, help='number of patches evaluated in each shape (only for sequential_shapes_random_patches)')
     parser.add_argument('--query_points_per_patch', type=int, default=1, help='number of query points per patch')
     parser.add_argument('--sub_sample_size', type=int, default=500, help='unused: the training value is taken from the params file')
     parser.add_argument('--seed', type=int, default=40938661, help='manual seed')
@@ -76,8 +77,10 @@ def _check_supported(train_opt, eval_opt):
         raise ValueError('Unsupported symmetric operation: %s' % train_opt.sym_op)
     if getattr(train_opt, 'single_transformer', 0):
         raise ValueError('Unsupported option: single_transformer=1')
-    if eval_opt.sampling != 'full':
+    if eval_opt.sampling not in ('full', 'sequential_shapes_random_patches'):
         raise ValueError('Unknown sampling strategy: %s' % eval_opt.sampling)
+    if eval_opt.sampling != 'full' and eval_opt.reconstruction:
+        raise ValueError('Unsupported option: --sampling %s with --reconstruction (a partial band cannot be meshed)' % eval_opt.sampling)
 
 
 def _shape_names(indir, dataset):
@@ -160,6 +163,15 @@ def points_to_surf_eval(eval_opt):
         os.makedirs(model_out_dir, exist_ok=True)
         names = _shape_names(eval_opt.indir, eval_opt.dataset)
         print(f'evaluating {len(names)} shapes')
+        shape_patch_inds = None
+        if eval_opt.sampling == 'sequential_shapes_random_patches':     # points_to_surf_eval.py:130-136
+            counts = [int(np.load(os.path.join(eval_opt.indir, '05_query_pts', n + '.ply.npy'), mmap_mode='r').shape[0]) for n in names]
+            from types import SimpleNamespace
+            sampler = samplers.SequentialShapeRandomPointcloudPatchSampler(
+                SimpleNamespace(shape_names=names, shape_patch_count=counts), patches_per_shape=eval_opt.patches_per_shape,
+                seed=eval_opt.seed, sequential_shapes=True, identical_epochs=False)
+            list(iter(sampler))
+            shape_patch_inds = sampler.shape_patch_inds
         for si, name in enumerate(names):
             if si % world != rank:
                 continue
@@ -171,6 +183,10 @@ def points_to_surf_eval(eval_opt):
                 query_pts = ops.query_points(lin, eval_opt.query_grid_resolution).cpu().numpy()
             else:
                 query_pts = np.load(os.path.join(eval_opt.indir, '05_query_pts', name + '.ply.npy')).astype(np.float32)
+                if shape_patch_inds is not None:
+                    inds = np.asarray(shape_patch_inds[si], dtype=np.int64)
+                    query_pts = np.ascontiguousarray(query_pts[inds])
+                    np.savetxt(os.path.join(model_out_dir, name + '.idx'), inds, fmt='%d')   # points_to_surf_eval.py:292-294
                 sdf = _eval_given_queries(eng, train_opt, eval_opt, pts_dev, query_pts, dev)
             imp_surf_np_ms = sdf.cpu().numpy()
             os.makedirs(os.path.join(model_out_dir, 'eval'), exist_ok=True)

@@ -293,8 +293,39 @@ def gen_train():
         print('train_%s.npz written: losses %s, oracle == reference' % (variant, out['losses']))
 
 
+def gen_samplers():
+    """Index sequences of the reference's samplers (source/data_loader.py:71-176) on a fake data source."""
+    from types import SimpleNamespace
+    from points2surf_b200 import samplers as mine
+    ds = SimpleNamespace(shape_names=['a', 'b', 'c', 'd'], shape_patch_count=[50, 7, 120, 33])
+    out = {'shape_patch_count': np.array(ds.shape_patch_count)}
+    cases = {
+        'seq': (lambda m: m.SequentialPointcloudPatchSampler(ds)),
+        'ssr_seq_shapes': (lambda m: m.SequentialShapeRandomPointcloudPatchSampler(ds, patches_per_shape=20, seed=40938661, sequential_shapes=True, identical_epochs=False)),
+        'ssr_perm_shapes': (lambda m: m.SequentialShapeRandomPointcloudPatchSampler(ds, patches_per_shape=40, seed=3627473, sequential_shapes=False, identical_epochs=False)),
+        'ssr_identical': (lambda m: m.SequentialShapeRandomPointcloudPatchSampler(ds, patches_per_shape=10, seed=5, sequential_shapes=False, identical_epochs=True)),
+        'random': (lambda m: m.RandomPointcloudPatchSampler(ds, patches_per_shape=25, seed=3627473, identical_epochs=False)),
+        'random_identical': (lambda m: m.RandomPointcloudPatchSampler(ds, patches_per_shape=1000, seed=9, identical_epochs=True)),
+    }
+    for name, make in cases.items():
+        r, m = make(ref_dl), make(mine)
+        assert len(r) == len(m)
+        for epoch in range(2):
+            a, b = np.array(list(iter(r)), dtype=np.int64), np.array(list(iter(m)), dtype=np.int64)
+            assert np.array_equal(a, b), (name, epoch)
+            out['%s_epoch%d' % (name, epoch)] = a
+            if hasattr(r, 'shape_patch_inds') and r.shape_patch_inds is not None:
+                for si in range(4):
+                    assert np.array_equal(np.asarray(r.shape_patch_inds[si]), np.asarray(m.shape_patch_inds[si]))
+                    out['%s_epoch%d_inds%d' % (name, epoch, si)] = np.asarray(r.shape_patch_inds[si], dtype=np.int64)
+        out[name + '_len'] = np.array(len(r))
+    np.savez_compressed(os.path.join(HERE, 'samplers.npz'), **out)
+    print('samplers.npz written, mirror == reference')
+
+
 if __name__ == '__main__':
     gen_grid()
+    gen_samplers()
     gen_train()
     gen_evaluation()
     gen_volume()
