@@ -274,6 +274,57 @@ class TrainStep:
             self._stn_bwd(rec['qstn'], dq, False)
         self._rec = None
 
+    # ------------------------------------------------------------------------------------------ eval-mode forward
+    def evaluate(self, batch):
+        """`p2s_model.eval()` forward + compute_loss without gradients (the test batches interleaved with training,
+        points_to_surf_train.py:483-500): BatchNorm uses the running statistics, nothing is recorded or updated.
+        -> (logits [B,2], [loss_magnitude, loss_sign])."""
+        p = self.p
+        P, S = self.P, self.S
+
+        def lin(x, name, bn, relu):
+            z = p.gemm_nt(x, self.params[name + '.weight'], self.params[name + '.bias'])
+            if bn is None:
+                return z
+            rv = self.buffers[bn + '.running_var']
+            invstd = torch.rsqrt(rv + BN_EPS)
+            return p.bn_apply(z, self.buffers[bn + '.running_mean'], invstd, self.params[bn + '.weight'], self.params[bn + '.bias'], relu)
+
+        def stn(prefix, x, B, n):
+            h = lin(x, prefix + 'conv1', prefix + 'bn1', True)
+            h = lin(h, prefix + 'conv2', prefix + 'bn2', True)
+            h = lin(h, prefix + 'conv3', prefix + 'bn3', True)
+            g, _ = p.maxpool_fwd(h, B, n)
+            f = lin(g, prefix + 'fc1', prefix + 'bn4', True)
+            f = lin(f, prefix + 'fc2', prefix + 'bn5', True)
+            return lin(f, prefix + 'fc3', None, False)
+
+        def feat(prefix, pts, B, n):
+            a = lin(pts.reshape(B * n, 3), prefix + 'conv0a', prefix + 'bn0a', True)
+            hb = lin(a, prefix + 'conv0b', prefix + 'bn0b', True)
+            T = p.add_row_(stn(prefix + 'stn2.', hb, B, n), self._eye64).view(B, 64, 64)
+            h = p.gemm_nt(hb.view(B, n, 64), T).view(B * n, 64)
+            h = lin(h, prefix + 'conv1', prefix + 'bn1', True)
+            h = lin(h, prefix + 'conv2', prefix + 'bn2', True)
+            h = lin(h, prefix + 'conv3', prefix + 'bn3', False)
+            return p.maxpool_fwd(h, B, n)[0]
+
+        patch = batch['patch_pts_ps'].contiguous()
+        B = patch.shape[0]
+        sub = p.center(batch['pts_sub_sample_ms'].contiguous(), batch['imp_surf_query_point_ms'].contiguous())
+        if self.use_point_stn:
+            src = torch.cat((patch, sub), dim=1).contiguous() if self.shared else sub
+            n = P + S if self.shared else S
+            R = p.quat_to_rot(stn('point_stn.' if self.shared else 'feat_global.stn1.', src.reshape(B * n, 3), B, n))
+            sub, patch = p.gemm_nt(sub, R), p.gemm_nt(patch, R)
+        f_glob = lin(feat('feat_global.', sub, B, S), 'fc1_global', 'bn1_global', True)
+        f_loc = lin(feat('feat_local.', patch, B, P), 'fc1_local', 'bn1_local', True)
+        x = lin(torch.cat((f_loc, f_glob), dim=1).contiguous(), 'fc2', 'bn2', True)
+        x = lin(x, 'fc3', 'bn3', True)
+        logits = lin(x, 'fc4', None, False)
+        losses = compute_loss(logits, batch, self.outputs, self.loss_weights, self.fixed_radius, prims=p, need_grad=False)
+        return logits, losses
+
     def zero_grad(self):
         self.flat_grads.zero_()
 

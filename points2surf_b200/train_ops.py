@@ -85,6 +85,16 @@ class CudaPrims:
                                            1 if relu else 0, _ptr(y), _stream()))
         return y, mean, invstd
 
+    def bn_apply(self, z, mean, invstd, gamma, beta, relu):
+        """act(gamma (z - mean) invstd + beta) with given statistics (eval-mode BatchNorm: running mean / rsqrt(var + eps))."""
+        z = _f(z, 'z')
+        M, Cc = z.shape
+        y = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            check(self.lib.p2s_op_bn_apply(_ptr(z), M, Cc, _ptr(_f(mean, 'mean')), _ptr(_f(invstd, 'invstd')), _ptr(_f(gamma, 'gamma')),
+                                           _ptr(_f(beta, 'beta')), 1 if relu else 0, _ptr(y), _stream()))
+        return y
+
     def bn_backward(self, dy, z, y_mask, mean, invstd, gamma):
         """-> dz, dgamma, dbeta.  y_mask = forward output when a ReLU follows the BatchNorm, else None."""
         dy, z = _f(dy, 'dy'), _f(z, 'z')

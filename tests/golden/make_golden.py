@@ -323,8 +323,41 @@ def gen_samplers():
     print('samplers.npz written, mirror == reference')
 
 
+def gen_train_init():
+    """Default initialisation of PointsToSurfModel under a fixed torch seed (per-tensor sum + first entries) and the
+    defaults of the reference's training argument parser; points2surf_b200.points_to_surf_train must reproduce both."""
+    import json
+    from source import points_to_surf_train as ref_train
+    from points2surf_b200 import points_to_surf_train as mine
+    out = {}
+    for variant in ('vanilla', 'max', 'uniform'):
+        v = synth.VARIANTS[variant]
+        torch.manual_seed(3627473)
+        m = PointsToSurfModel(net_size_max=1024, num_points=300, output_dim=2, use_point_stn=v['use_point_stn'], use_feat_stn=True,
+                              sym_op='max', use_query_point=True, sub_sample_size=1000, do_augmentation=True,
+                              single_transformer=0, shared_transformation=v['shared_transformer'])
+        ref_sd = m.state_dict()
+        torch.manual_seed(3627473)
+        my_sd = mine.initial_state_dict(v['use_point_stn'], v['shared_transformer'], 1024, 2)
+        assert list(ref_sd.keys()) == list(my_sd.keys()), variant
+        for k in ref_sd:
+            assert ref_sd[k].shape == my_sd[k].shape and torch.equal(ref_sd[k], my_sd[k]), (variant, k)
+        names = [k for k in ref_sd if ref_sd[k].is_floating_point()]
+        out[variant + '_names'] = np.array(names)
+        out[variant + '_sums'] = np.array([float(ref_sd[k].double().sum()) for k in names])
+        out[variant + '_first'] = np.array([float(ref_sd[k].reshape(-1)[0]) for k in names])
+    ref_defaults = vars(ref_train.parse_arguments([]))
+    my_defaults = vars(mine.parse_arguments([]))
+    assert ref_defaults == my_defaults, {k: (ref_defaults.get(k), my_defaults.get(k)) for k in set(ref_defaults) | set(my_defaults)
+                                          if ref_defaults.get(k) != my_defaults.get(k)}
+    out['parser_defaults_json'] = np.array(json.dumps(ref_defaults, sort_keys=True))
+    np.savez_compressed(os.path.join(HERE, 'train_init.npz'), **out)
+    print('train_init.npz written: initialisation and parser defaults == reference')
+
+
 if __name__ == '__main__':
     gen_grid()
+    gen_train_init()
     gen_samplers()
     gen_train()
     gen_evaluation()

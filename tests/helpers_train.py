@@ -48,6 +48,10 @@ class TorchPrims:
             running_var.mul_(1 - momentum).add_(momentum * (var * M / max(M - 1, 1)).to(z.dtype))
         return (torch.relu(y) if relu else y), mean.to(z.dtype), invstd.to(z.dtype)
 
+    def bn_apply(self, z, mean, invstd, gamma, beta, relu):
+        y = (gamma * invstd) * (z - mean) + beta
+        return torch.relu(y) if relu else y
+
     def bn_backward(self, dy, z, y_mask, mean, invstd, gamma):
         g = dy if y_mask is None else dy * (y_mask > 0)
         M = z.shape[0]

@@ -238,3 +238,23 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert float((moved_e - moved_g).norm()) <= 5e-2 * float(moved_e.norm())
     assert int(graph.buffers['bn2.num_batches_tracked']) == 102 and graph.steps_done == 2
     close(graph.buffers['bn2.running_mean'], eager.buffers['bn2.running_mean'], 1e-3, 'running mean after graph steps')
+
+
+@pytest.mark.skipif(__import__('os').environ.get('P2S_RUN_UNVERIFIED') != '1',
+                    reason='training-loop mirror on the GPU: written after the GPU budget of round 1 was spent; '
+                           'host logic is covered by tests/test_train_loop.py, run with P2S_RUN_UNVERIFIED=1')
+def test_training_loop_mirror_on_gpu(tmp_path):
+    import sys
+    sys.path.insert(0, __import__('os').path.dirname(__file__))
+    from test_train_loop import _make_dataset
+    from points2surf_b200 import points_to_surf_train as p2s_train
+    root = str(tmp_path / 'data')
+    _make_dataset(root, ['s0', 's1', 's2'], n_pts=2000, n_query=64)
+    opt = p2s_train.parse_arguments([
+        '--name', 'test', '--indir', root, '--outdir', str(tmp_path / 'models'), '--logdir', str(tmp_path / 'logs'),
+        '--nepoch', '2', '--batchSize', '16', '--patches_per_shape', '32', '--points_per_patch', '300', '--sub_sample_size', '1000',
+        '--patch_radius', '0.0', '--lr', '0.001', '--shared_transformer', '1',
+        '--outputs', 'imp_surf_magnitude', 'imp_surf_sign', 'patch_pts_ids', 'p_index'])
+    hist = p2s_train.points_to_surf_train(opt)
+    assert len([h for h in hist if h[0] == 'train']) == 8 and all(np.isfinite(h[3]).all() for h in hist)
+    assert (tmp_path / 'models' / 'test_model.pth').exists()
