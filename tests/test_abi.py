@@ -88,3 +88,17 @@ def test_library_is_newer_than_its_sources():
     assert srcs
     newest = max(os.path.getmtime(f) for f in srcs)
     assert os.path.getmtime(_lib.LIB_PATH) >= newest, 'libp2s_b200.so is older than its sources'
+
+
+def test_product_never_imports_the_oracle_or_tests():
+    """oracle/ and tests/ are test infrastructure: nothing under points2surf_b200/ (nor bench.py's product arm) may
+    import them -- a product path routed through the oracle would void every parity claim."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r'^\s*(from|import)\s+(oracle|tests|helpers|helpers_train)\b', re.M)
+    for f in glob.glob(os.path.join(root, 'points2surf_b200', '**', '*.py'), recursive=True):
+        assert not pat.search(open(f).read()), f
+    # bench.py may use the oracle only inside the CPU legs
+    src = open(os.path.join(root, 'bench.py')).read()
+    body = src[src.index('def run_b200('):src.index("if __name__ == '__main__':")]
+    assert 'oracle' not in body.replace('oracle port', ''), 'run_b200 must not touch the oracle'
