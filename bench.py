@@ -125,7 +125,7 @@ def cpu_reference_rate(args, cloud, sd, n_queries, fc4_bias=None, threads=None, 
     t_net = time.perf_counter() - t0
     # candidate grid is a per-shape cost: charge the sample its share
     total = t_asm + t_net + t_grid * (n_queries / max(Q, 1))
-    return dict(value=n_queries / total, cores=max(threads, workers), threads=threads, workers=workers, Q=Q, t_assemble_s=t_asm,
+    return dict(value=n_queries / total, cores=cores, threads=threads, workers=workers, Q=Q, t_assemble_s=t_asm,
                 t_network_s=t_net, t_grid_s=t_grid, sdf_checksum=float(np.abs(sdf).sum()))
 
 
@@ -177,6 +177,23 @@ def workload_config(args, Q):
             'queries_per_shape': int(Q), 'l2': 'flushed between timed iterations (256 MiB write)'}
 
 
+def calibrate_output_bias(sd, model, device_index):
+    """Centre the output bias of the rand-init checkpoint on a calibration batch (GPU fp32 path) so that the sign
+    classes are mixed; modifies `sd` in place and returns the new bias.  tests/test_gpu_headline.py builds the
+    bench's exact checkpoint through this function."""
+    import torch
+    from points2surf_b200 import ops, synth
+    v = synth.VARIANTS[model]
+    dev = torch.device('cuda', device_index)
+    eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=device_index, precision='fp32')
+    cal = synth.make_model_inputs(64, seed=777)
+    raw = eng.forward(*(torch.from_numpy(cal[k]).to(dev) for k in ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms')))
+    fc4_bias = (sd['fc4.bias'].numpy() - raw.median(dim=0).values.cpu().numpy()).astype(np.float32)
+    eng.close()
+    sd['fc4.bias'] = torch.from_numpy(fc4_bias)
+    return fc4_bias
+
+
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -225,13 +242,7 @@ def run_b200(args):
         precision = 'tc'
     guard = args.guard_band if args.guard_band is not None else (0.05 if precision == 'tc' else 0.0)
 
-    # calibrate the output bias on the GPU (fp32 path) so the rand-init net has mixed sign classes
-    eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision='fp32')
-    cal = synth.make_model_inputs(64, seed=777)
-    raw = eng.forward(*(torch.from_numpy(cal[k]).to(dev) for k in ('patch_pts_ps', 'pts_sub_sample_ms', 'imp_surf_query_point_ms')))
-    fc4_bias = (sd['fc4.bias'].numpy() - raw.median(dim=0).values.cpu().numpy()).astype(np.float32)
-    eng.close()
-    sd['fc4.bias'] = torch.from_numpy(fc4_bias)
+    fc4_bias = calibrate_output_bias(sd, args.model, local_rank)
     eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
 
     pts = torch.from_numpy(cloud).to(dev)

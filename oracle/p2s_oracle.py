@@ -166,9 +166,24 @@ def _t(sd, name):
     return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))
 
 
+_CONV_TF32 = False   # set (temporarily) by model_forward(conv_tf32=True)
+
+
+def _round_tf32(t):
+    """Round-to-nearest-even to TF32 (10 explicit mantissa bits): what the tensor cores behind cuDNN's default
+    `torch.backends.cudnn.allow_tf32 = True` Conv1d path do to both conv operands on Ampere and later."""
+    import torch
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return i.view(torch.float32)
+
+
 def _conv_bn(sd, x, conv, bn, relu=True):
     import torch.nn.functional as F
-    y = F.conv1d(x, _t(sd, conv + '.weight'), _t(sd, conv + '.bias'))
+    w = _t(sd, conv + '.weight')
+    if _CONV_TF32:
+        x, w = _round_tf32(x), _round_tf32(w)
+    y = F.conv1d(x, w, _t(sd, conv + '.bias'))
     y = F.batch_norm(y, _t(sd, bn + '.running_mean'), _t(sd, bn + '.running_var'),
                      _t(sd, bn + '.weight'), _t(sd, bn + '.bias'), training=False, eps=1e-5)
     return F.relu(y) if relu else y
@@ -279,18 +294,27 @@ def _model_forward_impl(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_poin
     x = torch.cat((patch_feat, shape_feat), dim=1)                           # :346
     x = _fc_bn(sd, x, 'fc2', 'bn2')
     x = _fc_bn(sd, x, 'fc3', 'bn3')
+    aux['fc3_out'] = x.numpy()
     x = _fc_bn(sd, x, 'fc4', None, relu=False)
     out = x.numpy()
     return (out, aux) if return_aux else out
 
 
 def model_forward(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms,
-                  use_point_stn=True, shared_transformer=True, return_aux=False):
-    """PointsToSurfModel.forward in eval mode, without autograd (see _model_forward_impl)."""
+                  use_point_stn=True, shared_transformer=True, return_aux=False, conv_tf32=False):
+    """PointsToSurfModel.forward in eval mode, without autograd (see _model_forward_impl).
+    conv_tf32=True emulates the reference's stock GPU arithmetic on Ampere+ (cuDNN Conv1d with TF32 operands,
+    fp32 accumulate; nn.Linear / bmm stay fp32 because torch.backends.cuda.matmul.allow_tf32 defaults to False):
+    the yardstick for the tensor-core engine's own deviation from the fp32 result."""
     import torch
-    with torch.no_grad():
-        return _model_forward_impl(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms, use_point_stn,
-                                   shared_transformer, return_aux)
+    global _CONV_TF32
+    prev, _CONV_TF32 = _CONV_TF32, bool(conv_tf32)
+    try:
+        with torch.no_grad():
+            return _model_forward_impl(sd, patch_pts_ps, pts_sub_sample_ms, imp_surf_query_point_ms, use_point_stn,
+                                       shared_transformer, return_aux)
+    finally:
+        _CONV_TF32 = prev
 
 
 # --------------------------------------------------------------------------------------

@@ -4,8 +4,12 @@
 //   propagate_sign               source/sdf.py:114-178
 //   clamp                        source/sdf.py:200-202
 // Signs are int8; the box sums are exact integers (the reference's float sums of {-1,0,1} are too), so the
-// result is bit-identical to the reference.  L2/HBM-bound byte work: per iteration res^3 * ~10 B.
+// result is bit-identical to the reference.  Sign propagation is one persistent cooperative kernel over a work list of
+// tiles along the propagating front (see propagate_kernel); section 8d counts it as res^3 * 2 B per iteration.
 #include "common.cuh"
+#include <algorithm>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace p2s {
 
@@ -22,19 +26,17 @@ __global__ void sdf_from_logits_kernel(const float* __restrict__ logits, const f
     sdf[i] = v;
 }
 
-__global__ void scatter_kernel(const int32_t* __restrict__ lin, const float* __restrict__ sdf, int64_t Q,
-                               float* __restrict__ vol) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Q) vol[lin[i]] = sdf[i];
-}
 
 struct Ctrl {
-    unsigned long long cnt[2];  // zero count of S, double-buffered by iteration parity
-    unsigned long long cntN;    // zero count of the thresholded neighbourhood vote
-    int done;
-    int iters;                  // applied iterations
-    int all_zero;               // every sample is exactly 0 (sdf.py:187-189)
-    unsigned nonzero_seen;
+    unsigned long long cntS0;   // zero count of the initial sign volume
+    long long dN[3];            // per-iteration change of the vote's zero count   (rotating, see propagate_kernel)
+    long long dS[3];            // per-iteration change of the sign volume's zero count
+    unsigned listCount[3];      // rotating tile work lists
+    int iters;                  // applied iterations (result)
+    int final_buf;              // which ping-pong buffer holds the final signs (result)
+    int error;                  // 1: iteration cap hit
+    unsigned nonzero_seen;      // some sample is not exactly 0 (sdf.py:187-189)
+    unsigned bad_index;         // scatter: number of voxel indices outside [0, res^3)
 };
 
 __global__ void any_nonzero_kernel(const float* __restrict__ sdf, int64_t Q, Ctrl* c) {
@@ -43,8 +45,7 @@ __global__ void any_nonzero_kernel(const float* __restrict__ sdf, int64_t Q, Ctr
     if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&c->nonzero_seen, 1u);
 }
 
-// block-wide sum of v, ONE atomic per block (a same-address atomic per warp serialises: res^3 / 32 of them cost
-// ~0.25 ms per kernel at 256^3).  Every thread of the block must call it.
+// block-wide sum of v, ONE atomic per block.  Every thread of the block must call it.
 __device__ __forceinline__ void block_count_add(unsigned v, unsigned long long* dst) {
     __shared__ unsigned warp_sum[32];
 #pragma unroll
@@ -59,200 +60,205 @@ __device__ __forceinline__ void block_count_add(unsigned v, unsigned long long* 
     }
 }
 
-// S = sign(vol), U0 = (S == 0), then the six border faces of vol (not of S) are set to -1  (sdf.py:144-154)
-__global__ void init_sign_kernel(float* __restrict__ vol, int res, int8_t* __restrict__ S, uint8_t* __restrict__ U0, Ctrl* c) {
+// Sign byte: bits 0-1 = sign in two's complement (0, +1 = 1, -1 = 3), bit 2 = "unknown at the start" (U0).
+constexpr uint8_t kU0 = 4u;
+__device__ __forceinline__ int sign_of(uint8_t b) { return (int)((int8_t)(b << 6)) >> 6; }
+
+// A = (sign(vol), U0 = (sign == 0)), then the six border faces of vol (not of the signs) are set to -1  (sdf.py:144-154)
+__global__ void init_sign_kernel(float* __restrict__ vol, int res, uint8_t* __restrict__ A, Ctrl* c) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t V = (int64_t)res * res * res;
     unsigned z = 0;
     if (v < V) {
         float x = vol[v];
-        int8_t s = x > 0.f ? 1 : (x < 0.f ? -1 : 0);
-        S[v] = s;
-        U0[v] = (s == 0);
+        int s = x > 0.f ? 1 : (x < 0.f ? -1 : 0);
+        A[v] = (uint8_t)((s & 3) | (s == 0 ? kU0 : 0));
         z = (s == 0);
         int iz = (int)(v % res), iy = (int)((v / res) % res), ix = (int)(v / ((int64_t)res * res));
         if (ix == 0 || iy == 0 || iz == 0 || ix == res - 1 || iy == res - 1 || iz == res - 1) vol[v] = -1.0f;
     }
-    block_count_add(z, &c->cnt[0]);
+    block_count_add(z, &c->cntS0);
 }
 
-// 1-D box sum along one axis with replicated edges: out[o] = sum_{t=lo..hi} in[clamp(o+t)]
-template <int AXIS>
-__global__ void box_axis_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int res, int lo, int hi,
-                                Ctrl* c, int iter) {
-    if (c->done) return;
-    if (AXIS == 2 && c->cnt[iter & 1] == 0) {  // `if unknown_before.sum() == 0: break`  (sdf.py:157-159)
-        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
-        return;
-    }
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t V = (int64_t)res * res * res;
-    if (AXIS == 2 && v == 0) { c->cntN = 0; c->cnt[(iter + 1) & 1] = 0; }
-    if (v >= V) return;
-    int iz = (int)(v % res), iy = (int)((v / res) % res), ix = (int)(v / ((int64_t)res * res));
-    int pos = AXIS == 2 ? iz : (AXIS == 1 ? iy : ix);
-    int64_t stride = AXIS == 2 ? 1 : (AXIS == 1 ? res : (int64_t)res * res);
-    const int8_t* base = in + v - (int64_t)pos * stride;
-    int acc = 0;
-    for (int t = lo; t <= hi; ++t) {
-        int p = min(max(pos + t, 0), res - 1);
-        acc += base[(int64_t)p * stride];
-    }
-    out[v] = (int8_t)acc;
+// iteration 0 evaluates every tile
+__global__ void init_tiles_kernel(int* __restrict__ list0, int* __restrict__ voteZeros, int numTiles, Ctrl* c) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < numTiles) { list0[t] = t; voteZeros[t] = 0; }
+    if (t == 0) c->listCount[0] = (unsigned)numTiles;
 }
 
-// last axis (x) fused with the certainty threshold, sign and the zero count of the vote (sdf.py:162-172)
-__global__ void box_x_vote_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ vote, int res, int lo, int hi,
-                                  float thr, Ctrl* c) {
-    if (c->done) return;
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t V = (int64_t)res * res * res;
-    unsigned z = 0;
-    if (v < V) {
-        int ix = (int)(v / ((int64_t)res * res));
-        int64_t stride = (int64_t)res * res;
-        const int8_t* base = in + v - (int64_t)ix * stride;
-        int acc = 0;
-        for (int t = lo; t <= hi; ++t) {
-            int p = min(max(ix + t, 0), res - 1);
-            acc += base[(int64_t)p * stride];
+// ---- iterative sign propagation (sdf.py:156-178) as ONE persistent cooperative kernel -----------------------------------
+// The reference recomputes the 5^3 box vote of the whole volume in every iteration (~0.3 res iterations).  A vote only changes
+// where a sign inside its box changed in the previous iteration, and signs change only along the propagating front, so the
+// kernel keeps a work list of 8x8x32-voxel tiles whose neighbourhood changed and re-evaluates only those; the zero counts
+// behind the reference's two stop rules (`unknown_before.sum() == 0`, `unknown_after.sum() >= unknown_before.sum()`) are
+// maintained incrementally (per-tile zero count of the vote, deltas of the sign zero count), so decisions and iteration
+// counts are identical to the full recomputation.  Signs ping-pong between two byte volumes: a tile that is not on the work
+// list has identical content in both (its last evaluation reproduced its input), a listed tile rewrites the output volume
+// completely, and a rejected last iteration is discarded by picking the input volume.  One grid-wide barrier per iteration;
+// the stop rule never leaves the device.
+constexpr int TX = 8, TY = 8, TZ = 32, kPropThreads = 256;
+
+struct PropParams {
+    uint8_t* buf[2];
+    int* list[3];
+    uint8_t* flags[2];
+    int* voteZeros;
+    Ctrl* ctrl;
+    int res, lo, hi, ntx, nty, ntz, maxIters;
+    float thr;
+};
+
+__global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int res = p.res, hl = -p.lo, hh = p.hi, W = hl + hh + 1;
+    const int X0 = TX + hl + hh, Y0 = TY + hl + hh, Z0 = TZ + hl + hh;
+    uint8_t* s0 = smem;                                                 // [X0][Y0][Z0] sign bytes (with U0 flag)
+    int8_t* t1 = (int8_t*)(smem + ((X0 * Y0 * Z0 + 15) & ~15));         // [X0][Y0][TZ] z sums (|.| <= 11)
+    int16_t* t2 = (int16_t*)((uint8_t*)t1 + ((X0 * Y0 * TZ + 15) & ~15));   // [X0][TY][TZ] zy sums (|.| <= 121)
+    __shared__ int sh[8];   // 0 dS, 1 voteZeros, 2..7 changed bbox (min x,y,z, max x,y,z)
+    const int tid = threadIdx.x;
+    long long totalN = 0;                                               // zero count of the vote (whole volume)
+    long long totalS = (long long)__ldcg(&p.ctrl->cntS0);               // zero count of the signs
+    int iters = 0, final_buf = 0, error = 0;
+    for (int it = 0;; ++it) {
+        const int cur = it % 3, nxt = (it + 1) % 3;
+        if (totalS == 0) { final_buf = it & 1; break; }                 // `if unknown_before.sum() == 0: break`
+        if (it >= p.maxIters) { final_buf = it & 1; error = 1; break; }
+        if (blockIdx.x == 0 && tid == 0) {                              // recycle the accumulators of iteration it+1 / it+2
+            p.ctrl->dN[nxt] = 0; p.ctrl->dS[nxt] = 0; p.ctrl->listCount[(it + 2) % 3] = 0;
         }
-        int8_t s = 0;
-        if (!(fabsf((float)acc) < thr)) s = acc > 0 ? 1 : (acc < 0 ? -1 : 0);
-        vote[v] = s;
-        z = (s == 0);
-    }
-    block_count_add(z, &c->cntN);
-}
-
-// `if unknown_after.sum() >= unknown_before.sum(): break` else S[U0] = vote[U0]   (sdf.py:175-177)
-__global__ void apply_vote_kernel(int8_t* __restrict__ S, const uint8_t* __restrict__ U0, const int8_t* __restrict__ vote,
-                                  int64_t V, Ctrl* c, int iter) {
-    if (c->done) return;
-    // cntN / cnt[iter&1] are final here (previous kernels completed); every thread takes the same branch
-    if (c->cntN >= c->cnt[iter & 1]) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
-        return;
-    }
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned z = 0;
-    if (v < V) {
-        int8_t s = S[v];
-        if (U0[v]) { s = vote[v]; S[v] = s; }
-        z = (s == 0);
-    }
-    block_count_add(z, &c->cnt[(iter + 1) & 1]);
-    if (v == 0) atomicAdd(&c->iters, 1);
-}
-
-// ---- word-wide variants (res % 4 == 0): one thread = 4 consecutive z voxels packed in a 32-bit word, per-byte SIMD adds
-// (sums stay within int8: |S| <= 1, three axes of at most 11 taps each only when sigma <= 5: 5^3 = 125; larger sigma use
-// the scalar kernels) and grid-stride loops (a few thousand counter atomics per kernel instead of one per 256 voxels).
-template <int AXIS>   // 2: z (inside the word and its neighbours), 1: y
-__global__ void __launch_bounds__(256)
-box_axis4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int res, int lo, int hi, Ctrl* c, int iter) {
-    if (c->done) return;
-    if (AXIS == 2 && c->cnt[iter & 1] == 0) {  // `if unknown_before.sum() == 0: break`  (sdf.py:157-159)
-        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
-        return;
-    }
-    if (AXIS == 2 && blockIdx.x == 0 && threadIdx.x == 0) { c->cntN = 0; c->cnt[(iter + 1) & 1] = 0; }
-    const unsigned rw = (unsigned)res >> 2;
-    const unsigned W = (unsigned)res * (unsigned)res * rw;
-    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
-        const unsigned wz = w % rw, row = w / rw;
-        if (AXIS == 2) {
-            const uint32_t* r = in + (size_t)row * rw;
-            // bytes b[8 + j] = position 4*wz + j, j in [-8, 11], replicated at the row ends
-            int b[20];
-            const int dmin = lo < -4 ? -2 : (lo < 0 ? -1 : 0), dmax = hi > 4 ? 2 : (hi > 0 ? 1 : 0);
-            const uint32_t first = r[0] & 0xffu, last = r[rw - 1] >> 24;
-#pragma unroll
-            for (int d = -2; d <= 2; ++d) {
-                uint32_t x = 0;
-                if (d >= dmin && d <= dmax) {
-                    const int wi = (int)wz + d;
-                    x = wi < 0 ? first * 0x01010101u : (wi >= (int)rw ? last * 0x01010101u : r[wi]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) b[4 * (d + 2) + i] = (int)(int8_t)(x >> (8 * i));
+        // (selects instead of indexing the parameter struct: a runtime index would spill it to local memory)
+        const uint8_t* __restrict__ in = (it & 1) ? p.buf[1] : p.buf[0];
+        uint8_t* __restrict__ out = (it & 1) ? p.buf[0] : p.buf[1];
+        const int count = (int)__ldcg(&p.ctrl->listCount[cur]);
+        const int* list = cur == 0 ? p.list[0] : (cur == 1 ? p.list[1] : p.list[2]);
+        int* listNext = nxt == 0 ? p.list[0] : (nxt == 1 ? p.list[1] : p.list[2]);
+        uint8_t* flagCur = (it & 1) ? p.flags[1] : p.flags[0];
+        uint8_t* flagNext = (it & 1) ? p.flags[0] : p.flags[1];
+        for (int k = blockIdx.x; k < count; k += gridDim.x) {
+            const int tile = __ldcg(&list[k]);
+            const int tz = tile % p.ntz, ty = (tile / p.ntz) % p.nty, tx = tile / (p.ntz * p.nty);
+            const int bx = tx * TX, by = ty * TY, bz = tz * TZ;
+            if (tid < 8) sh[tid] = tid < 2 ? 0 : (tid < 5 ? 1 << 20 : -1);
+            if (tid == 0) flagCur[tile] = 0;
+            // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration
+            for (int i = tid; i < X0 * Y0 * Z0; i += kPropThreads) {
+                const int z = i % Z0, xy = i / Z0, y = xy % Y0, x = xy / Y0;
+                const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1), gz = min(max(bz + z - hl, 0), res - 1);
+                s0[i] = __ldcg(in + ((size_t)gx * res + gy) * res + gz);
             }
-            uint32_t o = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            __syncthreads();
+            for (int i = tid; i < X0 * Y0 * TZ; i += kPropThreads) {       // sum along z
+                const int z = i & (TZ - 1), xy = i >> 5;
+                const uint8_t* r = s0 + xy * Z0 + z;
                 int acc = 0;
+                for (int t = 0; t < W; ++t) acc += sign_of(r[t]);
+                t1[i] = (int8_t)acc;
+            }
+            __syncthreads();
+            for (int i = tid; i < X0 * TZ; i += kPropThreads) {            // sum along y, sliding window
+                const int z = i & (TZ - 1), x = i >> 5;
+                const int8_t* r = t1 + (x * Y0) * TZ + z;
+                int acc = 0;
+                for (int t = 0; t < W; ++t) acc += r[t * TZ];
+                t2[(x * TY) * TZ + z] = (int16_t)acc;
+                for (int y = 1; y < TY; ++y) {
+                    acc += r[(y + W - 1) * TZ] - r[(y - 1) * TZ];
+                    t2[(x * TY + y) * TZ + z] = (int16_t)acc;
+                }
+            }
+            __syncthreads();
+            {                                                              // sum along x, threshold, apply
+                const int z = tid & (TZ - 1), y = tid >> 5;
+                const int gy = by + y, gz = bz + z;
+                const bool col_ok = gy < res && gz < res;
+                const int16_t* r = t2 + y * TZ + z;
+                int acc = 0;
+                for (int t = 0; t < W; ++t) acc += r[t * TY * TZ];
+                int dS = 0, nz = 0, cminx = 1 << 20, cmaxx = -1;
+                for (int x = 0; x < TX; ++x) {
+                    if (x > 0) acc += r[(x + W - 1) * TY * TZ] - r[(x - 1) * TY * TZ];
+                    const int gx = bx + x;
+                    if (col_ok && gx < res) {
+                        int vote = 0;
+                        if (!(fabsf((float)acc) < p.thr)) vote = acc > 0 ? 1 : (acc < 0 ? -1 : 0);
+                        nz += (vote == 0);
+                        const uint8_t b = s0[((x + hl) * Y0 + (y + hl)) * Z0 + z + hl];
+                        uint8_t nb = b;
+                        if (b & kU0) {
+                            const int so = sign_of(b);
+                            nb = (uint8_t)((vote & 3) | kU0);
+                            if (vote != so) { dS += (vote == 0) - (so == 0); cminx = min(cminx, x); cmaxx = max(cmaxx, x); }
+                        }
+                        out[((size_t)gx * res + gy) * res + gz] = nb;
+                    }
+                }
+                // block totals
+                unsigned ch = __ballot_sync(0xffffffffu, cmaxx >= 0);
 #pragma unroll
-                for (int t = -5; t <= 5; ++t)           // static indices: b[] stays in registers
-                    if (t >= lo && t <= hi) acc += b[8 + k + t];
-                o |= ((uint32_t)acc & 0xffu) << (8 * k);
+                for (int o = 16; o > 0; o >>= 1) { dS += __shfl_xor_sync(0xffffffffu, dS, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
+                if ((tid & 31) == 0) { if (dS) atomicAdd(&sh[0], dS); if (nz) atomicAdd(&sh[1], nz); }
+                if (ch) {                                                  // rare: signs change only along the front
+                    if (cmaxx >= 0) {
+                        atomicMin(&sh[2], cminx); atomicMax(&sh[5], cmaxx);
+                        atomicMin(&sh[3], y); atomicMax(&sh[6], y);
+                        atomicMin(&sh[4], z); atomicMax(&sh[7], z);
+                    }
+                }
             }
-            out[w] = o;
-        } else {
-            const unsigned iy = row % (unsigned)res, ix = row / (unsigned)res;
-            uint32_t acc = 0;
-            for (int t = lo; t <= hi; ++t) {
-                const int p = min(max((int)iy + t, 0), res - 1);
-                acc = __vadd4(acc, in[((size_t)ix * res + p) * rw + wz]);
+            __syncthreads();
+            if (tid == 0) {
+                const int old = __ldcg(&p.voteZeros[tile]);
+                if (sh[1] != old) { p.voteZeros[tile] = sh[1]; atomicAdd((unsigned long long*)&p.ctrl->dN[cur], (unsigned long long)(long long)(sh[1] - old)); }
+                if (sh[0]) atomicAdd((unsigned long long*)&p.ctrl->dS[cur], (unsigned long long)(long long)sh[0]);
             }
-            out[w] = acc;
+            if (sh[5] >= 0 && tid < 27) {
+                // a changed sign at local c moves the votes at c-hh .. c+hl: neighbours whose voxels fall in that range
+                const int dz = tid % 3 - 1, dy = (tid / 3) % 3 - 1, dx = tid / 9 - 1;
+                const bool rx = dx == 0 || (dx < 0 ? sh[2] - hh < 0 : sh[5] + hl >= TX);
+                const bool ry = dy == 0 || (dy < 0 ? sh[3] - hh < 0 : sh[6] + hl >= TY);
+                const bool rz = dz == 0 || (dz < 0 ? sh[4] - hh < 0 : sh[7] + hl >= TZ);
+                const int nx = tx + dx, ny = ty + dy, nzt = tz + dz;
+                if (rx && ry && rz && nx >= 0 && ny >= 0 && nzt >= 0 && nx < p.ntx && ny < p.nty && nzt < p.ntz) {
+                    const int n = (nx * p.nty + ny) * p.ntz + nzt;
+                    // byte flags, word-wide atomic: set our byte, see whether it was clear
+                    unsigned* wptr = (unsigned*)(flagNext + (n & ~3));
+                    const unsigned bit = 1u << (8 * (n & 3));
+                    if (!(atomicOr(wptr, bit) & bit)) listNext[atomicAdd(&p.ctrl->listCount[nxt], 1u)] = n;
+                }
+            }
+            __syncthreads();
         }
+        grid.sync();
+        totalN += __ldcg(&p.ctrl->dN[cur]);
+        const long long afterS = totalS + __ldcg(&p.ctrl->dS[cur]);
+        if (totalN >= totalS) { final_buf = it & 1; break; }            // `if unknown_after.sum() >= unknown_before.sum(): break`
+        totalS = afterS;
+        ++iters;
     }
+    if (blockIdx.x == 0 && tid == 0) { p.ctrl->iters = iters; p.ctrl->final_buf = final_buf; p.ctrl->error = error; }
 }
 
-__global__ void __launch_bounds__(256)
-box_x_vote4_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ vote, int res, int lo, int hi, float thr, Ctrl* c) {
-    if (c->done) return;
-    const unsigned rw = (unsigned)res >> 2;
-    const unsigned plane = (unsigned)res * rw;         // words per x plane
-    const unsigned W = (unsigned)res * plane;
-    unsigned z = 0;
-    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
-        const unsigned ix = w / plane, rem = w - ix * plane;
-        uint32_t acc = 0;
-        for (int t = lo; t <= hi; ++t) {
-            const int p = min(max((int)ix + t, 0), res - 1);
-            acc = __vadd4(acc, in[(size_t)p * plane + rem]);
-        }
-        uint32_t o = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int a = (int)(int8_t)(acc >> (8 * k));
-            int s = 0;
-            if (!(fabsf((float)a) < thr)) s = a > 0 ? 1 : (a < 0 ? -1 : 0);
-            o |= ((uint32_t)s & 0xffu) << (8 * k);
-            z += (s == 0);
-        }
-        vote[w] = o;
-    }
-    block_count_add(z, &c->cntN);
-}
-
-__global__ void __launch_bounds__(256)
-apply_vote4_kernel(uint32_t* __restrict__ S, const uint32_t* __restrict__ U0, const uint32_t* __restrict__ vote, unsigned W,
-                   Ctrl* c, int iter) {
-    if (c->done) return;
-    if (c->cntN >= c->cnt[iter & 1]) {       // `if unknown_after.sum() >= unknown_before.sum(): break`
-        if (blockIdx.x == 0 && threadIdx.x == 0) c->done = 1;
-        return;
-    }
-    unsigned z = 0;
-    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
-        const uint32_t m = __vcmpne4(U0[w], 0u);          // 0xff where the voxel was unknown at the start
-        const uint32_t s = S[w];
-        const uint32_t n = (vote[w] & m) | (s & ~m);
-        if (n != s) S[w] = n;
-        z += (unsigned)__popc(__vcmpeq4(n, 0u)) >> 3;
-    }
-    block_count_add(z, &c->cnt[(iter + 1) & 1]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->iters, 1);
+// the reference raises IndexError for an index >= res and wraps a negative one (sdf.py:95-111); here both are counted and
+// reported as an error by the entry point, nothing is written out of bounds
+__global__ void scatter_kernel(const int32_t* __restrict__ lin, const float* __restrict__ sdf, int64_t Q, int64_t V,
+                               float* __restrict__ vol, Ctrl* c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    const int32_t l = lin[i];
+    if (l >= 0 && (int64_t)l < V) vol[l] = sdf[i];
+    else atomicAdd(&c->bad_index, 1u);
 }
 
 // vol[vol == 0] = S[vol == 0]; clamp to [-1, 1]   (sdf.py:179,200-202)
-__global__ void finalize_kernel(float* __restrict__ vol, const int8_t* __restrict__ S, int64_t V) {
+__global__ void finalize_kernel(float* __restrict__ vol, const uint8_t* __restrict__ A, const uint8_t* __restrict__ B,
+                                const Ctrl* __restrict__ c, int64_t V) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     float x = vol[v];
-    if (x == 0.0f) x = (float)S[v];
+    if (x == 0.0f) x = (float)sign_of((c->final_buf ? B : A)[v]);
     x = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);
     vol[v] = x;
 }
@@ -272,54 +278,58 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     P2S_CHECK(sigma >= 1 && sigma <= 11, "sigma out of range [1, 11]");
     const int64_t V = (int64_t)res * res * res;
     const unsigned blocks = (unsigned)cdiv(V, 256);
-    size_t off_S = 256, off_U0 = off_S + V, off_t1 = off_U0 + V, off_t2 = off_t1 + V, off_vote = off_t2 + V;
-    uint8_t* base = (uint8_t*)t_vol_ws.get(off_vote + V);
+    PropParams pp{};
+    pp.res = res;
+    // convolve(ones(sigma^3), mode='nearest'): output o sums inputs o-ceil(s/2)+1 .. o+floor(s/2)
+    pp.lo = -((sigma + 1) / 2) + 1; pp.hi = sigma / 2; pp.thr = thr;
+    pp.ntx = (int)cdiv(res, TX); pp.nty = (int)cdiv(res, TY); pp.ntz = (int)cdiv(res, TZ);
+    pp.maxIters = 64 * res;
+    const int numTiles = pp.ntx * pp.nty * pp.ntz;
+    const size_t nt4 = ((size_t)numTiles + 3) & ~(size_t)3;
+    size_t off = 256;
+    const size_t off_A = off; off += (V + 255) & ~(size_t)255;
+    const size_t off_B = off; off += (V + 255) & ~(size_t)255;
+    const size_t off_lists = off; off += 3 * nt4 * sizeof(int);
+    const size_t off_vz = off; off += nt4 * sizeof(int);
+    const size_t off_flags = off; off += 2 * nt4;
+    uint8_t* base = (uint8_t*)t_vol_ws.get(off);
     Ctrl* ctrl = (Ctrl*)base;
-    int8_t* S = (int8_t*)(base + off_S);
-    uint8_t* U0 = base + off_U0;
-    int8_t* t1 = (int8_t*)(base + off_t1);
-    int8_t* t2 = (int8_t*)(base + off_t2);
-    int8_t* vote = (int8_t*)(base + off_vote);
+    pp.ctrl = ctrl;
+    pp.buf[0] = base + off_A; pp.buf[1] = base + off_B;
+    for (int i = 0; i < 3; ++i) pp.list[i] = (int*)(base + off_lists) + (size_t)i * nt4;
+    pp.voteZeros = (int*)(base + off_vz);
+    pp.flags[0] = base + off_flags; pp.flags[1] = base + off_flags + nt4;
 
     P2S_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
     P2S_CUDA(cudaMemsetAsync(vol, 0, (size_t)V * sizeof(float), st));
     if (Q > 0) {
         P2S_LAUNCH(any_nonzero_kernel, (unsigned)cdiv(Q, 256), 256, 0, st, sdf, Q, ctrl);
-        P2S_LAUNCH(scatter_kernel, (unsigned)cdiv(Q, 256), 256, 0, st, lin_idx, sdf, Q, vol);
+        P2S_LAUNCH(scatter_kernel, (unsigned)cdiv(Q, 256), 256, 0, st, lin_idx, sdf, Q, V, vol, ctrl);
     }
-    P2S_LAUNCH(init_sign_kernel, blocks, 256, 0, st, vol, res, S, U0, ctrl);
-    // convolve(ones(sigma^3), mode='nearest'): output o sums inputs o-ceil(s/2)+1 .. o+floor(s/2)
-    const int lo = -((sigma + 1) / 2) + 1, hi = sigma / 2;
-    // word-wide kernels: 4 z voxels per thread, needs word-aligned rows and box sums that fit int8 (sigma^3 <= 127)
-    const bool words = (res % 4 == 0) && sigma <= 5;
-    int dev_id = 0, sms = 148;
+    P2S_LAUNCH(init_sign_kernel, blocks, 256, 0, st, vol, res, pp.buf[0], ctrl);
+    P2S_CUDA(cudaMemsetAsync(pp.flags[0], 0, 2 * nt4, st));
+    P2S_LAUNCH(init_tiles_kernel, (unsigned)cdiv(numTiles, 256), 256, 0, st, pp.list[0], pp.voteZeros, numTiles, ctrl);
+
+    // persistent cooperative launch: as many CTAs as are co-resident (the runtime refuses a larger grid instead of hanging)
+    const int hl = -pp.lo, hh = pp.hi;
+    const int X0 = TX + hl + hh, Y0 = TY + hl + hh, Z0 = TZ + hl + hh;
+    const size_t smem = (size_t)((X0 * Y0 * Z0 + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
+    int dev_id = 0, sms = 148, per_sm = 0;
     P2S_CUDA(cudaGetDevice(&dev_id));
     P2S_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
-    const unsigned wblocks = (unsigned)std::min<int64_t>(cdiv(V / 4, 256), (int64_t)sms * 8);
+    P2S_CUDA(cudaFuncSetAttribute(propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel, kPropThreads, smem));
+    P2S_CHECK(per_sm >= 1, "sign propagation kernel does not fit on an SM");
+    const unsigned grid = (unsigned)std::max(1, std::min(numTiles, sms * per_sm));
+    void* args[] = {&pp};
+    P2S_CUDA(cudaLaunchCooperativeKernel((const void*)propagate_kernel, dim3(grid), dim3(kPropThreads), args, smem, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    P2S_LAUNCH(finalize_kernel, blocks, 256, 0, st, vol, pp.buf[0], pp.buf[1], ctrl, V);
     Ctrl h{};
-    int iter = 0;
-    const int kBatch = 8;
-    for (;;) {
-        for (int b = 0; b < kBatch; ++b, ++iter) {
-            if (words) {
-                P2S_LAUNCH(box_axis4_kernel<2>, wblocks, 256, 0, st, (const uint32_t*)S, (uint32_t*)t1, res, lo, hi, ctrl, iter);
-                P2S_LAUNCH(box_axis4_kernel<1>, wblocks, 256, 0, st, (const uint32_t*)t1, (uint32_t*)t2, res, lo, hi, ctrl, iter);
-                P2S_LAUNCH(box_x_vote4_kernel, wblocks, 256, 0, st, (const uint32_t*)t2, (uint32_t*)vote, res, lo, hi, thr, ctrl);
-                P2S_LAUNCH(apply_vote4_kernel, wblocks, 256, 0, st, (uint32_t*)S, (const uint32_t*)U0, (const uint32_t*)vote,
-                           (unsigned)(V / 4), ctrl, iter);
-                continue;
-            }
-            P2S_LAUNCH(box_axis_kernel<2>, blocks, 256, 0, st, S, t1, res, lo, hi, ctrl, iter);
-            P2S_LAUNCH(box_axis_kernel<1>, blocks, 256, 0, st, t1, t2, res, lo, hi, ctrl, iter);
-            P2S_LAUNCH(box_x_vote_kernel, blocks, 256, 0, st, t2, vote, res, lo, hi, thr, ctrl);
-            P2S_LAUNCH(apply_vote_kernel, blocks, 256, 0, st, S, U0, vote, V, ctrl, iter);
-        }
-        P2S_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-        P2S_CUDA(cudaStreamSynchronize(st));
-        if (h.done) break;
-        P2S_CHECK(iter < 64 * res, "sign propagation did not converge");
-    }
-    P2S_LAUNCH(finalize_kernel, blocks, 256, 0, st, vol, S, V);
+    P2S_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    P2S_CUDA(cudaStreamSynchronize(st));
+    P2S_CHECK(h.bad_index == 0, "voxel index outside [0, res^3): query points must lie in [-1, 1)^3 (the reference raises IndexError / wraps)");
+    P2S_CHECK(h.error == 0, "sign propagation did not converge");
     if (iterations_host) *iterations_host = h.iters;
     if (Q > 0 && !h.nonzero_seen) {
         // the reference prints a warning and returns without writing anything (sdf.py:187-189)

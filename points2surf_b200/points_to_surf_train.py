@@ -219,11 +219,15 @@ def _assemble_batch(dataset, indices, assembler, rng, device, dtype=torch.float3
     return {k: v.to(dtype) for k, v in batch.items()}
 
 
-def calc_metrics(pred, batch):
-    """abs_dist_rms and the sign-classification scores of source/points_to_surf_train.py:566-598 (magnitude + sign)."""
+def calc_metrics(pred, batch, fixed_radius=False):
+    """abs_dist_rms and the sign-classification scores of source/points_to_surf_train.py:566-598 (magnitude + sign).
+    The reference's compute_loss divides batch_data['imp_surf_magnitude_ms'] by the patch radius IN PLACE
+    (points_to_surf_train.py:552-555) before calc_metrics reads it, so the logged rmse is against the normalised target;
+    this mirror does not mutate the batch and applies the same normalisation here."""
     from . import evaluation
     abs_dist = torch.tanh(pred[:, 0]).pow(2)
-    rms = torch.sqrt(torch.mean((abs_dist.abs() - batch['imp_surf_magnitude_ms'].abs()) ** 2))
+    target = batch['imp_surf_magnitude_ms'] if fixed_radius else batch['imp_surf_magnitude_ms'] / batch['patch_radius_ms']
+    rms = torch.sqrt(torch.mean((abs_dist.abs() - target.abs()) ** 2))
     inside = torch.where(pred[:, 1] >= 0.0, torch.ones_like(abs_dist), -torch.ones_like(abs_dist))
     out = evaluation.compare_predictions_binary_tensors(ground_truth=batch['imp_surf_dist_sign_ms'], predicted=inside,
                                                         prediction_name='training_metrics')
@@ -259,21 +263,31 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
     """Train like source/points_to_surf_train.py:165-535.  `prims` / `assembler` / `device` / `dtype` exist for the
     CPU tests of the host logic; the product path leaves them at their defaults (CUDA primitives, GPU assembly)."""
     _check_supported(opt)
+    # data parallelism: one process per GPU (torchrun); each rank trains on its slice of every batch, gradients are
+    # averaged by TrainStep's all_reduce, BatchNorm statistics stay per rank like the reference's nn.DataParallel replicas
+    # (points_to_surf_train.py:412-413).  Rank 0 alone prompts, logs and writes files.
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
     if device is None:
         if not torch.cuda.is_available() or opt.gpu_idx[0] < 0:
             raise RuntimeError('points2surf_b200 needs a CUDA device (--gpu_idx >= 0): there is no CPU fallback')
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if world > 1:
             device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
         else:
+            if len(opt.gpu_idx) > 1:
+                raise ValueError('--gpu_idx lists %d devices: multi-GPU training runs one process per GPU here '
+                                 '(python -m torch.distributed.run --nproc-per-node N ...), not nn.DataParallel threads' % len(opt.gpu_idx))
             device = torch.device('cuda', opt.gpu_idx[0])
         torch.cuda.set_device(device)
-    print('Training on 1 devices:\n  %s' % str(device))
+    is_main = rank == 0
+    print('Training on %d devices:\n  %s' % (world, str(device)))
 
     log_dirname = os.path.join(opt.logdir, opt.name)
     params_filename = os.path.join(opt.outdir, '%s_params.pth' % opt.name)
     model_filename = os.path.join(opt.outdir, '%s_model.pth' % opt.name)
     desc_filename = os.path.join(opt.outdir, '%s_description.txt' % opt.name)
-    if os.path.exists(log_dirname) or os.path.exists(model_filename):
+    if is_main and (os.path.exists(log_dirname) or os.path.exists(model_filename)):
         if opt.name != 'test':
             response = input('A training run named "{}" already exists, overwrite? (y/n) '.format(opt.name))
             if response != 'y':
@@ -317,31 +331,40 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
     os.makedirs(opt.outdir, exist_ok=True)
 
     writer = None
-    try:
-        from torch.utils.tensorboard import SummaryWriter
-        writer = SummaryWriter(log_dirname, comment=opt.name)
-        writer.add_scalar('LR', opt.lr, 0)
-    except Exception:       # tensorboard is optional here
-        writer = None
+    if is_main:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(log_dirname, comment=opt.name)
+            writer.add_scalar('LR', opt.lr, 0)
+        except Exception:       # tensorboard is optional here
+            writer = None
 
     ts = TrainStep({k: v.to(device) for k, v in state.items()}, opt.use_point_stn, opt.shared_transformer,
                    points_per_patch=opt.points_per_patch, sub_sample_size=opt.sub_sample_size, net_size=opt.net_size, lr=opt.lr,
                    momentum=opt.momentum, device=device, prims=prims, outputs=tuple(output_names),
                    output_loss_weights=output_loss_weights, fixed_radius=False, dtype=dtype)
     if assembler is None:
-        assembler = GpuAssembler(device, opt.points_per_patch, opt.sub_sample_size, opt.uniform_subsample, opt.seed)
-    rng_aug = np.random.RandomState(opt.seed)
+        assembler = GpuAssembler(device, opt.points_per_patch, opt.sub_sample_size, opt.uniform_subsample, opt.seed + rank)
+    rng_aug = np.random.RandomState(opt.seed + rank)            # augmentation / sub-sample streams differ per rank
 
-    torch.save(opt, params_filename)
-    with open(desc_filename, 'w+') as text_file:
-        print(opt.desc, file=text_file)
+    if is_main:
+        torch.save(opt, params_filename)
+        with open(desc_filename, 'w+') as text_file:
+            print(opt.desc, file=text_file)
 
     green = lambda x: '\033[92m' + x + '\033[0m'
     blue = lambda x: '\033[94m' + x + '\033[0m'
+    # the reference builds a fresh MultiStepLR after a --refine resume (points_to_surf_train.py:406-410): milestones count
+    # scheduler steps since the (re)start, the first epoch always runs at opt.lr
     lr = opt.lr
     history = []
     for epoch in range(start_epoch, opt.nepoch):
-        train_batches, test_batches = _batches(train_sampler, opt.batchSize), _batches(test_sampler, opt.batchSize)
+        # every rank draws the same index sequence (same sampler seed) and takes its slice of each batch
+        train_batches = [b[rank::world] for b in _batches(train_sampler, opt.batchSize)]
+        test_batches = [b[rank::world] for b in _batches(test_sampler, opt.batchSize)]
+        if world > 1 and any(len(b) == 0 for b in train_batches + test_batches):
+            raise ValueError('batchSize %d leaves a rank without queries in the last batch: use a batch size that is a '
+                             'multiple of the world size %d' % (opt.batchSize, world))
         test_batchind, test_fraction_done = -1, 0.0
         for train_batchind, indices in enumerate(train_batches):
             batch = _assemble_batch(train_set, indices, assembler, rng_aug, device, dtype)
@@ -365,13 +388,13 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
                     writer.add_scalar('loss/eval/total', sum(float(l) for l in tl), step)
                 history.append(('test', epoch, test_batchind, [float(l) for l in tl]))
 
-        if epoch % opt.save_interval == 0 or epoch == opt.nepoch - 1:
+        if is_main and (epoch % opt.save_interval == 0 or epoch == opt.nepoch - 1):
             torch.save(_prefixed(ts.state_dict()), model_filename)
-        if epoch % (5 * 10 ** math.floor(math.log10(max(2, epoch - 1)))) == 0 or epoch % 100 == 0 or epoch == opt.nepoch - 1:
+        if is_main and (epoch % (5 * 10 ** math.floor(math.log10(max(2, epoch - 1)))) == 0 or epoch % 100 == 0 or epoch == opt.nepoch - 1):
             torch.save(_prefixed(ts.state_dict()), os.path.join(opt.outdir, '%s_model_%d.pth' % (opt.name, epoch)))
 
         # MultiStepLR(milestones=scheduler_steps, gamma=0.1), stepped once per epoch (points_to_surf_train.py:519-529)
-        new_lr = opt.lr * (0.1 ** sum(1 for m in opt.scheduler_steps if epoch + 1 >= m))
+        new_lr = opt.lr * (0.1 ** sum(1 for m in opt.scheduler_steps if epoch - start_epoch + 1 >= m))
         if new_lr != lr:
             print('LR changed from {} to {} in epoch {}'.format(lr, new_lr, epoch))
         lr = new_lr

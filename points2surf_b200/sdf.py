@@ -37,6 +37,10 @@ def implicit_surface_to_mesh(query_dist_ms, query_pts_ms, volume_out_file, mc_ou
         return
     dev = _device()
     idx = model_space_to_volume_space(np.asarray(query_pts_ms), grid_res)
+    if idx.size and (idx.min() < 0 or idx.max() >= grid_res):
+        # the reference raises IndexError for an index >= grid_res and silently wraps a negative one
+        # (sdf.py:95-111, SURVEY section 10 "Precondition"); both are rejected here, nothing is written out of bounds
+        raise IndexError('query points outside [-1, 1)^3: voxel index out of range for grid resolution %d' % grid_res)
     lin = torch.from_numpy(((idx[:, 0] * grid_res + idx[:, 1]) * grid_res + idx[:, 2]).astype(np.int32)).to(dev)
     sdf = torch.from_numpy(np.ascontiguousarray(query_dist_ms, dtype=np.float32)).to(dev)
     start = time.time()

@@ -9,6 +9,7 @@ affine parameters / running statistics are randomised, all from a NumPy legacy
 RandomState so that the same seed gives the same checkpoint on any box.
 """
 import argparse
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -66,10 +67,29 @@ def make_state_dict_numpy(variant='vanilla', seed=0, net=1024, module_prefix='')
     return sd
 
 
-def make_state_dict(variant='vanilla', seed=0, net=1024, module_prefix=''):
+FITTED_FC4 = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fitted_fc4.npz')
+
+
+def fitted_fc4(variant, seed):
+    """Last layer (fc4 weight [2,128], bias [2]) fitted on a 10k-point sphere so that the otherwise rand-init
+    checkpoint `make_state_dict(variant, seed)` produces a surface-like SDF (tests/golden/make_e2e_golden.py: ridge
+    regression on the fc3 activations against the analytic signed distance; everything in front of fc4 stays random).
+    Only the (variant, seed) pairs the file was fitted for are available."""
+    f = np.load(FITTED_FC4)
+    if variant + '_seed' not in f or int(f[variant + '_seed']) != int(seed):
+        raise ValueError('no fitted fc4 for (%s, seed %d) in %s' % (variant, seed, FITTED_FC4))
+    return f[variant + '_weight'].copy(), f[variant + '_bias'].copy()
+
+
+def make_state_dict(variant='vanilla', seed=0, net=1024, module_prefix='', fitted=False):
     import torch
-    return OrderedDict((k, torch.from_numpy(v.copy())) for k, v in
-                       make_state_dict_numpy(variant, seed, net, module_prefix).items())
+    sd = OrderedDict((k, torch.from_numpy(v.copy())) for k, v in
+                     make_state_dict_numpy(variant, seed, net, module_prefix).items())
+    if fitted:
+        w, b = fitted_fc4(variant, seed)
+        sd[module_prefix + 'fc4.weight'] = torch.from_numpy(w)
+        sd[module_prefix + 'fc4.bias'] = torch.from_numpy(b)
+    return sd
 
 
 def make_cloud(kind='sphere', n=10000, seed=0, noise=0.005):

@@ -12,6 +12,15 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
+def ids_checksum(ids):
+    """Order-sensitive 64-bit checksum of an int id matrix [Q,S] (shared with the tests)."""
+    a = np.asarray(ids, dtype=np.uint64)
+    w = (np.arange(a.shape[1], dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))[None, :]
+    rows = (a * w).sum(axis=1, dtype=np.uint64)
+    k = np.arange(a.shape[0], dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(7)
+    return int(np.bitwise_xor.reduce(rows * k))
+
+
 def golden_model_case(variant):
     """-> (state_dict (torch tensors, calibrated fc4 bias), inputs dict (numpy), golden npz)."""
     import torch

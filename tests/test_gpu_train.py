@@ -240,9 +240,6 @@ def test_cuda_graph_replay_matches_eager_steps():
     close(graph.buffers['bn2.running_mean'], eager.buffers['bn2.running_mean'], 1e-3, 'running mean after graph steps')
 
 
-@pytest.mark.skipif(__import__('os').environ.get('P2S_RUN_UNVERIFIED') != '1',
-                    reason='training-loop mirror on the GPU: written after the GPU budget of round 1 was spent; '
-                           'host logic is covered by tests/test_train_loop.py, run with P2S_RUN_UNVERIFIED=1')
 def test_training_loop_mirror_on_gpu(tmp_path):
     import sys
     sys.path.insert(0, __import__('os').path.dirname(__file__))
