@@ -162,7 +162,7 @@ def run_reference(args):
         'ms_per_step': 1e3 * args.cpu_sample / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, r['Q']),
-        'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': r['cores'], 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': r['cores'], 'threads_used': max(r['threads'], r['workers']), 'kind': 'port',
                          'sample': '%d queries evenly spaced over the %d-query band per step (oracle port: scipy cKDTree kNN + '
                                    'NumPy RandomState sub-sample in %d worker processes, torch-CPU fp32 network on %d threads)'
                                    % (args.cpu_sample, r['Q'], r['workers'], r['threads'])},
@@ -293,6 +293,10 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches
 
+    try:
+        peaks_hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:
+        peaks_hbm = 6576.1   # B200_PROFILING.md fallback (measured copy bandwidth of this pool)
     sampler = ClockSampler(local_rank)
     sampler.start()
     dev_ms, launches = timed(step_dev, args.steps, max(args.warmup, 3))
@@ -305,7 +309,13 @@ def run_b200(args):
     mesh_stage = None
     if not args.skip_mesh_stage:
         from points2surf_b200 import sharding
-        lin, sdf = step_dev()
+        # the timed checkpoint is rand-init (calibrated bias): its SDF describes no surface.  The mesh stage runs on the
+        # SDF of the same architecture with the fitted last layer (synth.fitted_fc4), so that sign propagation and
+        # marching cubes see a surface-like band and a real mesh comes out.
+        sd_fit = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4, fitted=True)
+        eng_fit = ops.Engine(sd_fit, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
+        lin, sdf = eng_fit.reconstruct(pts, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q)
+        eng_fit.close()
         res = args.grid_res
         for _ in range(2):
             vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
@@ -334,10 +344,11 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         vox = float(res) ** 3
         mesh_stage = {'sign_propagation_ms': t_vol, 'sign_propagation_iterations': int(iters),
-                      'sign_propagation_GBps': (vox * 10.0 * max(iters, 1) + vox * 13.0) / (t_vol * 1e-3) / 1e9,
+                      'sign_propagation_GBps': vox * 2.0 * (max(iters, 0) + 1) / (t_vol * 1e-3) / 1e9,
+                      'sign_propagation_frac_of_hbm_peak': vox * 2.0 * (max(iters, 0) + 1) / (t_vol * 1e-3) / 1e9 / float(peaks_hbm),
                       'marching_cubes_ms': t_mc, 'verts': int(mv.shape[0]), 'faces': int(mf.shape[0]),
                       'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + mv.shape[0] * 12.0 + mf.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
-                      'bytes_model': 'sign propagation: res^3 * (10 B per iteration + 13 B init/finalize); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
+                      'bytes_model': 'sign propagation: SURVEY 8d algorithmic bytes = res^3 * 2 B per vote evaluation (iterations + 1; the whole scatter/init/propagate/finalize call is timed); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
                       'mesh_gather_ms': float(tt[1].item()), 'meshes_on_rank0': gathered,
                       'shapes_per_s_incl_mesh': world * 1e3 / (dev_ms / args.steps + float(tt[0].item()) + float(tt[1].item()))}
     sampler.stop_flag = True
@@ -362,11 +373,7 @@ def run_b200(args):
         if prof and prof['launches'] > 0:
             peak = peaks.get('bf16_tflops_sustained') or 1400.0
             ach = prof['flops'] / (prof['ms'] * 1e-3) / 1e12
-            traffic = None
-            try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel
-                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_pass_traffic.json')))['traffic_bytes_per_launch_mean']
-            except Exception:
-                pass
+            traffic = None   # per-launch DRAM bytes come from an `ncu --set full` capture (profiles/), not from this run
             roofline = {'bound': 'tensor', 'kernel': prof['kernel'], 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                         'frac': ach / peak, 'traffic': traffic,
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
@@ -388,7 +395,7 @@ def run_b200(args):
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': roofline,
-            'cpu_baseline': {'value': cpu['value'], 'unit': 'queries/s', 'cores': cpu['cores'], 'kind': 'port',
+            'cpu_baseline': {'value': cpu['value'], 'unit': 'queries/s', 'cores': cpu['cores'], 'threads_used': max(cpu['threads'], cpu['workers']), 'kind': 'port',
                              'sample': '%d queries evenly spaced over the band (assembly in %d worker processes %.2fs, network on %d torch threads %.2fs)'
                                        % (args.cpu_sample, cpu['workers'], cpu['t_assemble_s'], cpu['threads'], cpu['t_network_s'])},
             'tensor_flops_per_s': value * FLOP_PER_QUERY[args.model],

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define P2S_ABI_VERSION 1
+#define P2S_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ library / errors ----------- */
 int p2s_abi_version(void);
@@ -105,7 +105,8 @@ int p2s_forward_host(p2s_model* m, const float* patch_pts_ps, const float* pts_s
                      const float* imp_surf_query_point_ms, int64_t B, float* logits);
 
 /* post_process + combine (source/sdf_nn.py:11-21, source/points_to_surf_eval.py:184-196,263-271,205-207):
- * sdf = tanh(l0)^2 * radius * (l1 >= 0 ? +1 : -1), NaN -> 1. */
+ * sdf = tanh(l0)^2 * radius * (l1 >= 0 ? +1 : -1), NaN -> 1.  patch_radius_ms == NULL is the fixed-radius case
+ * (train_opt.patch_radius > 0): the magnitude is not rescaled (points_to_surf_eval.py:188-189,364-368). */
 int p2s_sdf_from_logits_dev(const float* logits, const float* patch_radius_ms, int64_t B,
                             float* sdf, void* stream);
 
@@ -127,6 +128,19 @@ int p2s_query_points_dev(const int32_t* lin_idx, int64_t Q, int res, float* quer
  *   patch_ids [Q,k] (may be NULL)  patch_pts_ps [Q,k,3]  patch_radius_ms [Q] */
 int p2s_knn_patch_dev(const float* pts, int64_t N, const float* query_pts_ms, int64_t Q, int k,
                       int32_t* patch_ids, float* patch_pts_ps, float* patch_radius_ms, void* stream);
+
+/* point_cloud.get_patch_kdtree in ball-query mode (patch_radius > 0, the radius ablations
+ * experiments/train_p2s_{small,medium,large}_radius.sh) + the padding rule and fixed-radius normalisation of
+ * PointcloudPatchDataset.__getitem__ (source/base/point_cloud.py:176-192, source/data_loader.py:340-350):
+ * every point with float64 distance <= patch_radius (cKDTree.query_ball_point on the float32 coordinates); when there are
+ * more than k, a uniformly random k-subset without replacement (the reference's rng.choice; here the k smallest
+ * Philox clocks keyed by (seed, query index): same law, different stream, independent of batching); when there are fewer,
+ * the patch is padded with the query point (patch-space origin, id 0 like the reference's -1 -> 0).
+ *   patch_ids [Q,k] (may be NULL; ascending id when nothing is dropped)  patch_pts_ps [Q,k,3] = (p - q) / patch_radius
+ *   patch_radius_ms [Q] = patch_radius   in_ball_counts [Q] (may be NULL) = points found before sub-setting / padding */
+int p2s_ball_patch_dev(const float* pts, int64_t N, const float* query_pts_ms, int64_t Q, int64_t query_index_base,
+                       int k, double patch_radius, uint64_t seed, int32_t* patch_ids, float* patch_pts_ps,
+                       float* patch_radius_ms, int32_t* in_ball_counts, void* stream);
 
 /* utils.get_point_cloud_sub_sample (source/base/utils.py:196-227), N >= sub_sample_size.
  *   mode P2S_SUBSAMPLE_UNIFORM : with replacement, like rng.randint             (utils.py:213-216)
@@ -155,6 +169,8 @@ typedef struct {
     int32_t subsample_mode;   /* train_opt.uniform_subsample ? UNIFORM : WEIGHTED */
     int32_t batch;            /* queries per network batch (0 = library default) */
     uint64_t seed;            /* --seed                  */
+    float patch_radius;       /* train_opt.patch_radius: <= 0 kNN patches, > 0 ball-query patches of this radius */
+    int32_t reserved;         /* must be 0 */
 } p2s_recon_config;
 int p2s_reconstruct_dev(p2s_model* m, const p2s_recon_config* rc, const float* pts, int64_t N,
                         int64_t first_query, int64_t num_queries,

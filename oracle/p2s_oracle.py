@@ -109,6 +109,27 @@ def knn_patch(pts, kdtree, query_point, k):
     return ids, patch_ps.astype(np.float32), np.float32(radius)
 
 
+def ball_patch(pts, kdtree, query_point, patch_radius, points_per_patch, rng):
+    """Ball-query patch: source/base/point_cloud.py:176-192 (all points within patch_radius; a random subset when there
+    are too many -- consumes `rng` like the reference's dataset rng; -1 padding when there are too few) followed by the
+    padding rule and the fixed-radius normalisation of source/data_loader.py:340-350.
+    Returns (ids [P] int32 with pads set to 0, patch_pts_ps [P,3] f32, in-ball count)."""
+    ids = np.array(kdtree.query_ball_point(x=query_point, r=patch_radius), dtype=np.int32)
+    count = ids.shape[0]
+    if count > points_per_patch:
+        ids = ids[rng.choice(np.arange(count), points_per_patch, replace=False)]
+    if count < points_per_patch:
+        padding = np.full((points_per_patch - count), -1, dtype=np.int32)
+        ids = padding if count == 0 else np.concatenate((ids, padding), axis=0)
+    pad = ids == -1
+    ids[pad] = 0
+    pts_patch_ms = pts[ids, :]
+    pts_patch_ms[pad, :] = query_point
+    rep = np.repeat(np.expand_dims(query_point, axis=0), pts_patch_ms.shape[-2], axis=-2)
+    patch_ps = (pts_patch_ms - rep) / patch_radius
+    return ids, patch_ps.astype(np.float32), count
+
+
 def knn_bruteforce(pts, query_point, k):
     """Restatement of what cKDTree.query computes: Euclidean distances evaluated in float64 on
     the float32 coordinates; k smallest, ascending.  Returns (ids, d2_f64) with ties broken by id."""

@@ -17,7 +17,7 @@ class ModelConfig(C.Structure):
 
 class ReconConfig(C.Structure):
     _fields_ = [('res', C.c_int32), ('eps', C.c_int32), ('subsample_mode', C.c_int32), ('batch', C.c_int32),
-                ('seed', C.c_uint64)]
+                ('seed', C.c_uint64), ('patch_radius', C.c_float), ('reserved', C.c_int32)]
 
 
 PRECISION_FP32, PRECISION_TC = 0, 1
@@ -44,6 +44,7 @@ SIGNATURES = {
     'p2s_query_grid_dev': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, C.POINTER(_i64), _vp]),
     'p2s_query_points_dev': (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     'p2s_knn_patch_dev': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'p2s_ball_patch_dev': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, C.c_double, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     'p2s_subsample_dev': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, C.c_uint64, _vp, _vp]),
     'p2s_gather_points_dev': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'p2s_reconstruct_dev': (C.c_int, [_vp, C.POINTER(ReconConfig), _vp, _i64, _i64, _i64, _vp, _vp, _i64,
@@ -91,7 +92,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError here means the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.p2s_abi_version() != 1:
+    if lib.p2s_abi_version() != 2:
         raise P2SError('libp2s_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -10,6 +10,7 @@ std::atomic<uint64_t> g_launches{0};
 void query_grid(const float* pts, int64_t N, int res, int eps, int32_t* lin_idx, int64_t cap, int64_t* count_host, cudaStream_t st);
 void query_points(const int32_t* lin_idx, int64_t Q, int res, float* out, cudaStream_t st);
 void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids, float* patch, float* radius, cudaStream_t st);
+void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int k, double patch_radius, uint64_t seed, int32_t* ids, float* patch, float* radius, int32_t* counts, cudaStream_t st, const int32_t* qidx = nullptr);
 void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr);
 void gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
 void scatter_f32(const float* src, const int32_t* idx, int64_t n, float* dst, cudaStream_t st);
@@ -88,7 +89,7 @@ size_t blob_floats(const p2s_model_config& c) {
 
 void check_cfg(const p2s_model_config& c) {
     P2S_CHECK(c.net_size == 1024, "only net_size 1024 is supported");
-    P2S_CHECK(c.points_per_patch >= 8 && c.points_per_patch <= 512, "points_per_patch must be in [8, 512]");
+    P2S_CHECK(c.points_per_patch >= 8 && c.points_per_patch <= 1536, "points_per_patch must be in [8, 1536]");
     P2S_CHECK(c.sub_sample_size >= 8 && c.sub_sample_size <= 4096, "sub_sample_size must be in [8, 4096]");
 }
 
@@ -110,7 +111,8 @@ void forward(Model& m, const float* patch, const float* sub, const float* query,
 
 static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, int64_t N, int64_t first_query,
                         int64_t num_queries, int32_t* lin_idx, float* sdf, int64_t cap, int64_t* Q_host, cudaStream_t st) {
-    P2S_CHECK(rc.res >= 2 && rc.eps >= 1, "bad reconstruction config");
+    P2S_CHECK(rc.res >= 2 && rc.eps >= 1 && rc.reserved == 0, "bad reconstruction config");
+    const bool fixed_radius = rc.patch_radius > 0.f;      // ball-query patches: |d| is not rescaled (points_to_surf_eval.py:364-368)
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
     int64_t Qall = 0;
     const int64_t vox = (int64_t)rc.res * rc.res * rc.res;
@@ -146,7 +148,9 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
     }
     auto assemble = [&](const int32_t* lin, int64_t n, int64_t qbase, const int32_t* qidx) {
         query_points(lin, n, rc.res, b.qpts, st);
-        { StageScope t("assemble: knn_patch", st); knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
+        { StageScope t("assemble: knn_patch", st);
+          if (fixed_radius) ball_patch(pts, N, b.qpts, n, qbase, P, (double)rc.patch_radius, rc.seed, nullptr, b.patch, b.radius, nullptr, st, qidx);
+          else knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
         // the Philox stream is keyed by the query's rank in the whole ordered list -> independent of slabs/batches
         { StageScope t("assemble: subsample+gather", st);
           subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx);
@@ -158,7 +162,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
             assemble(lin_idx + q0, n, first_query + q0, nullptr);
             m.guard_base = q0;
             forward(m, b.patch, b.sub, b.qpts, n, b.logits, st);
-            sdf_from_logits(b.logits, b.radius, n, sdf + q0, st);
+            sdf_from_logits(b.logits, fixed_radius ? nullptr : b.radius, n, sdf + q0, st);
         }
         if (defer_guard) {
             m.guard_list = nullptr;
@@ -175,7 +179,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
                 gather_i32(lin_idx, glist + g0, n, glin, st);
                 assemble(glin, n, first_query, glist + g0);
                 forward_guard(m, b.patch, b.sub, b.qpts, n, b.logits, st);
-                sdf_from_logits(b.logits, b.radius, n, gsdf, st);
+                sdf_from_logits(b.logits, fixed_radius ? nullptr : b.radius, n, gsdf, st);
                 scatter_f32(gsdf, glist + g0, n, sdf, st);
             }
         }
@@ -334,7 +338,7 @@ int p2s_forward_host(p2s_model* mm, const float* patch, const float* sub, const 
 
 int p2s_sdf_from_logits_dev(const float* logits, const float* radius, int64_t B, float* sdf, void* stream) {
     return guarded([&] {
-        P2S_CHECK(logits && radius && sdf, "null argument");
+        P2S_CHECK(logits && sdf, "null argument");
         sdf_from_logits(logits, radius, B, sdf, as_stream(stream));
     });
 }
@@ -359,6 +363,16 @@ int p2s_knn_patch_dev(const float* pts, int64_t N, const float* queries, int64_t
         knn_patch(pts, N, queries, Q, k, ids, patch, radius, as_stream(stream));
         int err = assemble_error_check(as_stream(stream));
         P2S_CHECK(err == 0, "degenerate cloud: more than 512 points tie at the k-th neighbour distance");
+    });
+}
+
+int p2s_ball_patch_dev(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int k, double patch_radius,
+                       uint64_t seed, int32_t* ids, float* patch, float* radius, int32_t* counts, void* stream) {
+    return guarded([&] {
+        P2S_CHECK(pts && queries && patch && radius, "null argument");
+        ball_patch(pts, N, queries, Q, qbase, k, patch_radius, seed, ids, patch, radius, counts, as_stream(stream));
+        int err = assemble_error_check(as_stream(stream));
+        P2S_CHECK(err == 0, "degenerate cloud: too many equal random keys at the ball-query selection boundary");
     });
 }
 

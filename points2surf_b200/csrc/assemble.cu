@@ -15,7 +15,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kBins = 2048;
-constexpr int kCap = 1024;  // boundary-bin candidates that are sorted exactly
+constexpr int kCap = 1024;  // boundary-bin candidates that are sorted exactly (sub-sampler, kNN up to 512 neighbours)
+constexpr int kCapBig = 2048;   // kNN with 513..1536 neighbours (large_kNN: 1200) and ball-query patches
 
 // ---- key helpers: non-negative doubles order like their bit patterns ----
 __device__ __forceinline__ unsigned long long dkey(double v) { return (unsigned long long)__double_as_longlong(v); }
@@ -25,19 +26,22 @@ __device__ __forceinline__ int bin0(unsigned long long key) {
     return (int)(b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b));
 }
 
-struct SelectSmem {
+template <int CAP>
+struct SelectSmemT {
     unsigned hist[kBins];
-    unsigned long long cand_key[kCap];
-    int cand_id[kCap];
+    unsigned long long cand_key[CAP];
+    int cand_id[CAP];
     int bin_sel[4];       // selected bin per level
     unsigned below;       // number of keys strictly below the boundary bin
     unsigned n_direct;    // slots used by "surely in" members
     unsigned n_cand;      // boundary candidates collected
     int levels;           // refinement levels used (1..3)
 };
+using SelectSmem = SelectSmemT<kCap>;
 
 // does `key` fall in the boundary bin chain selected so far (levels [0, upto))?
-__device__ __forceinline__ int chain_cmp(const SelectSmem& s, unsigned long long key, int upto) {
+template <int CAP>
+__device__ __forceinline__ int chain_cmp(const SelectSmemT<CAP>& s, unsigned long long key, int upto) {
     // returns -1 if key sorts below the chain, 0 if inside, +1 above
     int b = bin0(key);
     if (b != s.bin_sel[0]) return b < s.bin_sel[0] ? -1 : 1;
@@ -49,8 +53,8 @@ __device__ __forceinline__ int chain_cmp(const SelectSmem& s, unsigned long long
 }
 
 // Block-wide: find the bin chain that contains the k-th smallest key.  KeyFn(i) -> key of item i.
-template <class KeyFn>
-__device__ void find_boundary(SelectSmem& s, int N, int k, int cand_cap, KeyFn keyfn) {
+template <int CAP, class KeyFn>
+__device__ void find_boundary(SelectSmemT<CAP>& s, int N, int k, int cand_cap, KeyFn keyfn) {
     const int tid = threadIdx.x;
     if (tid == 0) { s.below = 0; s.levels = 0; }
     for (int level = 0; level < 3; ++level) {
@@ -97,10 +101,11 @@ __device__ void find_boundary(SelectSmem& s, int N, int k, int cand_cap, KeyFn k
 }
 
 // bitonic sort of (key, id) ascending over the first P = pow2ceil(n) slots (slots >= n are padded with +inf keys)
-__device__ void sort_candidates(SelectSmem& s, int n) {
+template <int CAP>
+__device__ void sort_candidates(SelectSmemT<CAP>& s, int n) {
     const int tid = threadIdx.x;
     int P = 64;
-    while (P < n) P <<= 1;                       // n <= kCap (checked by the callers), so P <= kCap
+    while (P < n) P <<= 1;                       // n <= CAP (checked by the callers), so P <= CAP
     for (int i = tid; i < P; i += kThreads)
         if (i >= n) { s.cand_key[i] = ~0ull; s.cand_id[i] = 0x7fffffff; }
     __syncthreads();
@@ -140,11 +145,13 @@ __device__ __forceinline__ float norm_f32(float dx, float dy, float dz) {
 // queries and overflowing candidate lists fall back to the histogram selection.
 constexpr int kRun = 8;
 
+template <int CAP>
 __global__ void __launch_bounds__(kThreads)
 knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int64_t Q, int k,
                  int32_t* __restrict__ ids_out, float* __restrict__ patch_out, float* __restrict__ radius_out,
                  int* __restrict__ err_flag) {
-    __shared__ SelectSmem s;
+    constexpr int kCap = CAP;                     // shadows the file-level constant inside this kernel
+    __shared__ SelectSmemT<CAP> s;
     __shared__ float red[kThreads / 32];
     __shared__ float s_radius;
     __shared__ double s_kth;          // exact k-th squared distance of the previous query (0 = unknown)
@@ -193,7 +200,7 @@ knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__
         if (!done) {
             // ---- histogram selection
             __syncthreads();
-            find_boundary(s, N, k, kCap - 512, keyfn);
+            find_boundary(s, N, k, kCap - (k > 512 ? k : 512), keyfn);
             if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
             __syncthreads();
             const int levels = s.levels;
@@ -262,12 +269,113 @@ knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1]
     return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
+
+// ------------------------------------------------------------------------------------------------
+// K2b: ball-query patches (radius ablations) -- point_cloud.get_patch_kdtree with patch_radius > 0
+// (source/base/point_cloud.py:176-192) + the padding rule of PointcloudPatchDataset.__getitem__
+// (source/data_loader.py:340-350): all points with float64 distance <= r (cKDTree.query_ball_point semantics on
+// float32 coordinates); more than k of them -> a uniformly random k-subset without replacement (rng.choice in the
+// reference; here the k smallest Philox clocks, same law, different stream); fewer -> padded with the query point itself
+// (patch-space origin, id 0).  Normalisation by the FIXED radius in float32.  One CTA per query.
+// Output order: ascending point id when nothing is dropped (the reference's order is the kd-tree traversal order; the
+// network max-pools over the patch, so order carries no information).
+constexpr int kBallMaxK = 1536;
+
+__global__ void __launch_bounds__(kThreads)
+ball_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int64_t qbase,
+                  const int32_t* __restrict__ qidx, int k, double r2, float rf, uint64_t seed,
+                  int32_t* __restrict__ ids_out, float* __restrict__ patch_out, float* __restrict__ radius_out,
+                  int32_t* __restrict__ count_out, int* __restrict__ err_flag) {
+    constexpr int CAP = kCapBig;
+    __shared__ SelectSmemT<CAP> s;
+    __shared__ int sel[kBallMaxK];
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const float qxf = queries[q * 3 + 0], qyf = queries[q * 3 + 1], qzf = queries[q * 3 + 2];
+    const double qx = qxf, qy = qyf, qz = qzf;
+    const uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
+    const float bound_f = (float)r2 * 1.00001f + 1e-30f;
+    auto in_ball = [&](int i) {
+        const float fx = pts[i * 3 + 0] - qxf, fy = pts[i * 3 + 1] - qyf, fz = pts[i * 3 + 2] - qzf;
+        if (fmaf(fx, fx, fmaf(fy, fy, fz * fz)) > bound_f) return false;       // fp32 pre-filter, exact test below
+        return dist2_f64(pts, i, qx, qy, qz) <= r2;
+    };
+    auto clock_key = [&](int i) {     // Exp(1) clock of point i for this query
+        uint32_t r[4];
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)(i >> 2), 0x3c6ef372u, r);
+        return dkey((double)(-__logf(u01_open(r[i & 3]))));
+    };
+    if (tid == 0) { s.n_cand = 0; s.n_direct = 0; }
+    __syncthreads();
+    for (int i = tid; i < N; i += kThreads) {
+        if (!in_ball(i)) continue;
+        const unsigned slot = atomicAdd(&s.n_cand, 1u);
+        if (slot < (unsigned)CAP) { s.cand_key[slot] = (unsigned long long)i; s.cand_id[slot] = i; }
+    }
+    __syncthreads();
+    const int count = (int)s.n_cand;
+    if (count_out && tid == 0) count_out[q] = count;
+    int n_sel = count < k ? count : k;
+    if (count <= k) {
+        sort_candidates(s, count);                            // ascending id
+        for (int j = tid; j < n_sel; j += kThreads) sel[j] = s.cand_id[j];
+    } else if (count <= CAP) {
+        for (int j = tid; j < count; j += kThreads) s.cand_key[j] = clock_key(s.cand_id[j]);
+        __syncthreads();
+        sort_candidates(s, count);
+        for (int j = tid; j < k; j += kThreads) sel[j] = s.cand_id[j];
+    } else {
+        // more points in the ball than the candidate buffer holds: histogram selection of the k smallest clocks
+        __syncthreads();
+        auto keyfn = [&](int i) { return in_ball(i) ? clock_key(i) : ~0ull; };
+        find_boundary(s, N, k, CAP, keyfn);
+        if (tid == 0) { s.n_direct = 0; s.n_cand = 0; }
+        __syncthreads();
+        const int levels = s.levels;
+        for (int i = tid; i < N; i += kThreads) {
+            const unsigned long long key = keyfn(i);
+            if (key == ~0ull) continue;
+            const int c = chain_cmp(s, key, levels);
+            if (c < 0) {
+                const unsigned slot = atomicAdd(&s.n_direct, 1u);
+                if (slot < (unsigned)k) sel[slot] = i;
+            } else if (c == 0) {
+                const unsigned slot = atomicAdd(&s.n_cand, 1u);
+                if (slot < (unsigned)CAP) { s.cand_key[slot] = key; s.cand_id[slot] = i; }
+            }
+        }
+        __syncthreads();
+        const unsigned n_direct = s.n_direct, n_cand = s.n_cand;
+        if (n_cand > (unsigned)CAP || n_direct != s.below || n_direct + n_cand < (unsigned)k) {
+            if (tid == 0) atomicExch(err_flag, 3);
+            return;
+        }
+        sort_candidates(s, (int)n_cand);
+        for (unsigned j = tid; n_direct + j < (unsigned)k; j += kThreads) sel[n_direct + j] = s.cand_id[j];
+    }
+    __syncthreads();
+    if (tid == 0) radius_out[q] = rf;
+    for (int j = tid; j < k; j += kThreads) {
+        float* o = patch_out + (q * k + j) * 3;
+        if (j < n_sel) {
+            const int id = sel[j];
+            if (ids_out) ids_out[q * k + j] = id;
+            o[0] = __fdiv_rn(__fsub_rn(pts[id * 3 + 0], qxf), rf);
+            o[1] = __fdiv_rn(__fsub_rn(pts[id * 3 + 1], qyf), rf);
+            o[2] = __fdiv_rn(__fsub_rn(pts[id * 3 + 2], qzf), rf);
+        } else {
+            if (ids_out) ids_out[q * k + j] = 0;              // -1 -> 0, coordinates <- query point (data_loader.py:341-345)
+            o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
 
 __global__ void subsample_uniform_kernel(int N, int64_t Q, int64_t qbase, const int32_t* __restrict__ qidx, int S, uint64_t seed, int32_t* __restrict__ out) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -460,10 +568,22 @@ int assemble_error_check(cudaStream_t st) {  // sync; returns and clears the dev
 void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids,
                float* patch, float* radius, cudaStream_t st) {
     P2S_CHECK(N >= k, "kNN needs N >= k (the reference returns out-of-range ids otherwise)");
-    P2S_CHECK(k >= 1 && k <= 512, "k must be in [1, 512]");
+    P2S_CHECK(k >= 1 && k <= kBallMaxK, "k must be in [1, 1536]");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
-    P2S_LAUNCH(knn_patch_kernel, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
+    if (k <= 512) P2S_LAUNCH(knn_patch_kernel<kCap>, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
+    else P2S_LAUNCH(knn_patch_kernel<kCapBig>, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
+}
+
+// the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q), like the sub-sampler's
+void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int k, double patch_radius,
+                uint64_t seed, int32_t* ids, float* patch, float* radius, int32_t* counts, cudaStream_t st, const int32_t* qidx) {
+    P2S_CHECK(patch_radius > 0.0, "ball query needs patch_radius > 0");
+    P2S_CHECK(k >= 1 && k <= kBallMaxK, "points_per_patch must be in [1, 1536]");
+    P2S_CHECK(N >= 1 && N < (1 << 30), "bad cloud size");
+    if (Q <= 0) return;
+    P2S_LAUNCH(ball_patch_kernel, (unsigned)Q, kThreads, 0, st, pts, (int)N, queries, qbase, qidx, k, patch_radius * patch_radius,
+               (float)patch_radius, seed, ids, patch, radius, counts, err_flag_dev());
 }
 
 // the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q)

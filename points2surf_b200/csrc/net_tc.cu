@@ -87,6 +87,7 @@ struct PassParams {
     const uint8_t* perq_img;   // [B] x 8192 B (precise: hi | lo, 16384 B)
     const uint8_t* w3_img;     // [8 chunks][32768 B] (precise: [8][hi | lo])  (K-major, LBO 128, SBO 2048)
     float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer)
+    long long* wstats;         // diagnostics: per-role barrier wait cycles (null = off)
 };
 
 struct Bars {
@@ -98,7 +99,8 @@ struct Bars {
 };
 static_assert(sizeof(Bars) <= 168, "barrier block");
 
-__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+// `acc` (diagnostics, P2S_TC_WAITSTATS=1): cycles this thread spent waiting are added to it
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, long long* acc = nullptr) {
 #if P2S_TC_BOUNDED_WAIT
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
@@ -107,9 +109,18 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
             __trap();
         }
     }
+    if (acc) *acc += clock64() - t0;
 #else
     mbar_wait(bar, parity);
 #endif
+}
+// wait statistics layout: [role 0..5][slot 0..7]; roles: 0 big-layer issuer, 1 mid issuer, 2 chain 0, 3 chain 1, 4 first layer,
+// 5 column-max epilogue; slots: 0 act2_full, 1 d3_empty, 2 dmid_free, 3 dmid_ready, 4 act2_empty, 5 a_free, 6 d3_full, 7 role cycles
+enum { WS_ACT2_FULL = 0, WS_D3_EMPTY, WS_DMID_FREE, WS_DMID_READY, WS_ACT2_EMPTY, WS_A_FREE, WS_D3_FULL, WS_TOTAL, WS_SLOTS };
+__device__ __forceinline__ void ws_flush(long long* g, int role, const long long* ws, long long t_begin) {
+    if (!g || (threadIdx.x & 31) != 0) return;
+    for (int i = 0; i < WS_TOTAL; ++i) if (ws[i]) atomicAdd((unsigned long long*)&g[role * WS_SLOTS + i], (unsigned long long)ws[i]);
+    atomicAdd((unsigned long long*)&g[role * WS_SLOTS + WS_TOTAL], (unsigned long long)(clock64() - t_begin));
 }
 
 // relu(a), relu(b) -> packed fp16x2 (low half = a), saturating
@@ -125,7 +136,7 @@ __device__ __forceinline__ void pack_relu_split(float a, float b, uint32_t& hi, 
     lo = pack_half2(fmaxf(a, 0.f) - hf.x, fmaxf(b, 0.f) - hf.y);
 }
 
-template <bool PRECISE>
+template <bool PRECISE, bool STATS = false>
 __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassParams p) {
     using C = Cfg<PRECISE>;
     constexpr uint32_t kOffMid = C::kOffMid, kOffAct2 = C::kOffAct2, kOffSmall = C::kOffSmall, kOffW3 = 0;
@@ -170,6 +181,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    long long ws[WS_TOTAL] = {0, 0, 0, 0, 0, 0, 0};
+    long long* const wsp = STATS ? ws : nullptr;            // STATS = false: everything below folds away
+    const long long t_begin = STATS ? clock64() : 0;
 
     if (warp == 8) {
         // =============================================================== big-layer MMA issuer (+ resident weight loads)
@@ -200,13 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             for (int it = 0; it < ntiles; ++it) {
                 // normal: tile t uses activation buffer t & 1; precise: one buffer (hi | lo) used by every tile
                 const uint32_t buf = PRECISE ? 0u : ((uint32_t)it & 1), buse = PRECISE ? (uint32_t)it : ((uint32_t)it >> 1);
-                wait_bar(&bars->act2_full[buf], buse & 1);
+                wait_bar(&bars->act2_full[buf], buse & 1, wsp ? wsp + WS_ACT2_FULL : nullptr);
                 const uint64_t db = dsc_act2 + (uint64_t)(buf * (kAct2Bytes >> 4));
 #pragma unroll
                 for (int c = 0; c < C::kChunks; ++c) {
                     const uint32_t g = (uint32_t)(it * C::kChunks + c);
                     const uint32_t stage = g & 1, use = g >> 1;
-                    wait_bar(&bars->d3_empty[stage], (use & 1) ^ 1);
+                    wait_bar(&bars->d3_empty[stage], (use & 1) ^ 1, wsp ? wsp + WS_D3_EMPTY : nullptr);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t da = dsc_w3 + (uint64_t)((uint32_t)c * (C::kChunkBytes >> 4));
@@ -277,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                     if (!mbar_test_wait_warp(&bars->a_ready[c], rn & 1)) return;
                     const bool small = !PRECISE && (p.mid_N[l] == 64);   // precise: the A operands occupy the small accumulator's columns
                     uint32_t& g_buf = small ? g_buf1 : g_buf0;
-                    if (g_buf > 0) wait_bar(&bars->dmid_free[small ? 1 : 0], (g_buf - 1) & 1);   // short: the previous read-out
+                    if (g_buf > 0) wait_bar(&bars->dmid_free[small ? 1 : 0], (g_buf - 1) & 1, wsp ? wsp + WS_DMID_FREE : nullptr);   // short: the previous read-out
                     tc_fence_after();
                     const uint32_t idesc = l == 0 ? idesc_mid0 : (l == 1 ? idesc_mid1 : idesc_mid2);
                     const uint64_t dsc = l == 0 ? dsc_mid0 : (l == 1 ? dsc_mid1 : dsc_mid2);
@@ -324,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             // ---- mid layers
             int boff = 0;
             for (int l = 0; l < p.num_mid; ++l, ++round) {
-                wait_bar(&bars->dmid_ready[c], round & 1);
+                wait_bar(&bars->dmid_ready[c], round & 1, wsp ? wsp + WS_DMID_READY : nullptr);
                 tc_fence_after();
                 const int N = p.mid_N[l];
                 const bool last = (l == p.num_mid - 1);
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
                 if (!last) {
                     tmem_st_wait();
-                    if (l == p.num_mid - 2) wait_bar(&bars->act2_empty[ab], (au & 1) ^ 1);
+                    if (l == p.num_mid - 2) wait_bar(&bars->act2_empty[ab], (au & 1) ^ 1, wsp ? wsp + WS_ACT2_EMPTY : nullptr);
                     tc_fence_before();
                     mbar_arrive(&bars->a_ready[c]);
                 } else {
@@ -463,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
             }
             if (it + 1 < ntiles) fetch(it + 1, x, y, z, pcx, pcy, pcz);     // next tile's point, in flight during the store
-            wait_bar(&bars->a_free[c], (((uint32_t)it >> 1) & 1) ^ 1);
+            wait_bar(&bars->a_free[c], (((uint32_t)it >> 1) & 1) ^ 1, wsp ? wsp + WS_A_FREE : nullptr);
             tc_fence_after();
             tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * C::kACols, v);
             if (PRECISE) {
@@ -473,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             tmem_st_wait();
             // never trigger the last mid layer's MMA before this chain's act2 buffer is free: its epilogue must not
             // hold the shared D_mid accumulator while waiting for the big layer
-            if (p.num_mid == 1) wait_bar(&bars->act2_empty[PRECISE ? 0 : c], ((PRECISE ? (uint32_t)it : ((uint32_t)it >> 1)) & 1) ^ 1);
+            if (p.num_mid == 1) wait_bar(&bars->act2_empty[PRECISE ? 0 : c], ((PRECISE ? (uint32_t)it : ((uint32_t)it >> 1)) & 1) ^ 1, wsp ? wsp + WS_ACT2_EMPTY : nullptr);
             tc_fence_before();
             mbar_arrive(&bars->a_ready[c]);
         }
@@ -493,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 for (int c = 0; c < C::kChunks; ++c) {
                     const uint32_t g = (uint32_t)(it * C::kChunks + c);
                     const uint32_t stage = g & 1, use = g >> 1;
-                    wait_bar(&bars->d3_full[stage], use & 1);
+                    wait_bar(&bars->d3_full[stage], use & 1, wsp ? wsp + WS_D3_FULL : nullptr);
                     tc_fence_after();
                     const uint32_t d = tmem + lane_base + kColD3 + stage * 128u;
                     float m = acc[c];
@@ -519,6 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             for (int c = 0; c < C::kChunks; ++c) p.out[(size_t)q * 1024 + (part * C::kChunks + c) * 128 + ch_lane] = acc[c];
         }
     }
+    if (STATS) ws_flush(p.wstats, warp == 8 ? 0 : (warp == 13 ? 1 : (warp < 4 ? 2 : (warp >= 14 ? 4 : (warp >= 9 ? 3 : 5)))), ws, t_begin);
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
@@ -723,7 +738,16 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
     p.perq_img = perq_img;
     p.w3_img = precise ? s.w3_img_p : s.w3_img;
     p.out = out;
+    p.wstats = nullptr;
     TcWeights& t = *m.tc;
+    static int wstats_on = -1;
+    if (wstats_on < 0) { const char* e = getenv("P2S_TC_WAITSTATS"); wstats_on = (e && e[0] == '1') ? 1 : 0; }
+    static long long* wstats_dev = nullptr;
+    if (wstats_on && !precise) {
+        if (!wstats_dev) P2S_CUDA(cudaMalloc(&wstats_dev, 6 * WS_SLOTS * sizeof(long long)));
+        P2S_CUDA(cudaMemsetAsync(wstats_dev, 0, 6 * WS_SLOTS * sizeof(long long), st));
+        p.wstats = wstats_dev;
+    }
     const int split = precise ? Cfg<true>::kSplit : Cfg<false>::kSplit;
     int streams = t.sm_count / split;
     if ((int64_t)streams > B) streams = (int)B;
@@ -735,7 +759,27 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
         P2S_CUDA(cudaEventRecord(e0, st));
     }
     if (precise) P2S_LAUNCH(pointnet_pass_kernel<true>, grid, kThreads, Cfg<true>::kSmemBytes, st, p);
-    else P2S_LAUNCH(pointnet_pass_kernel<false>, grid, kThreads, Cfg<false>::kSmemBytes, st, p);
+    else if (wstats_on) {
+        static bool attr = false;
+        if (!attr) { P2S_CUDA(cudaFuncSetAttribute(pointnet_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false>::kSmemBytes)); attr = true; }
+        P2S_LAUNCH((pointnet_pass_kernel<false, true>), grid, kThreads, Cfg<false>::kSmemBytes, st, p);
+    } else P2S_LAUNCH(pointnet_pass_kernel<false>, grid, kThreads, Cfg<false>::kSmemBytes, st, p);
+    if (wstats_on && !precise) {
+        // diagnostics: average wait cycles per warp of each role, as a share of the role's lifetime
+        long long h[6 * WS_SLOTS];
+        P2S_CUDA(cudaMemcpyAsync(h, wstats_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+        P2S_CUDA(cudaStreamSynchronize(st));
+        static const char* roles[6] = {"big-issuer", "mid-issuer", "chain0", "chain1", "first-layer", "colmax"};
+        static const char* slots[WS_TOTAL] = {"act2_full", "d3_empty", "dmid_free", "dmid_ready", "act2_empty", "a_free", "d3_full"};
+        fprintf(stderr, "p2s waitstats: pass num_mid=%d perq=%d pts=%d+%d B=%lld precise=%d grid=%d\n", s.num_mid, perq_layer, s0.n, s1.n, (long long)B, (int)precise, grid);
+        for (int r = 0; r < 6; ++r) {
+            const double tot = (double)h[r * WS_SLOTS + WS_TOTAL];
+            if (tot <= 0) continue;
+            fprintf(stderr, "   %-12s", roles[r]);
+            for (int i = 0; i < WS_TOTAL; ++i) if (h[r * WS_SLOTS + i]) fprintf(stderr, " %s %.1f%%", slots[i], 100.0 * (double)h[r * WS_SLOTS + i] / tot);
+            fprintf(stderr, "  (role cycles per warp %.0f)\n", tot / (grid * (r == 0 || r == 1 ? 1.0 : 4.0)));
+        }
+    }
     if (prof) {
         P2S_CUDA(cudaEventRecord(e1, st));
         t.prof_events.emplace_back(e0, e1);

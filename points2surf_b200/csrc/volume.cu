@@ -20,7 +20,8 @@ __global__ void sdf_from_logits_kernel(const float* __restrict__ logits, const f
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     float t = tanhf(logits[i * 2 + 0]);
-    float mag = __fmul_rn(__fmul_rn(t, t), radius[i]);
+    float mag = __fmul_rn(t, t);
+    if (radius) mag = __fmul_rn(mag, radius[i]);
     float v = logits[i * 2 + 1] >= 0.0f ? mag : -mag;
     if (isnan(v)) v = 1.0f;  // points_to_surf_eval.py:205-207
     sdf[i] = v;

@@ -71,8 +71,6 @@ def _check_supported(train_opt, eval_opt):
     outs = list(train_opt.outputs)
     if 'imp_surf' in outs or 'imp_surf_magnitude' not in outs or 'imp_surf_sign' not in outs:
         raise ValueError('Unsupported outputs %s: need imp_surf_magnitude + imp_surf_sign' % outs)
-    if getattr(train_opt, 'patch_radius', 0.0) > 0.0:
-        raise ValueError('Unsupported option: fixed-radius patches (patch_radius > 0)')
     if getattr(train_opt, 'sym_op', 'max') != 'max':
         raise ValueError('Unsupported symmetric operation: %s' % train_opt.sym_op)
     if getattr(train_opt, 'single_transformer', 0):
@@ -118,7 +116,12 @@ def _eval_given_queries(eng, train_opt, eval_opt, pts_dev, query_pts, dev):
     """Non-reconstruction pass (full_eval.py:31-41): queries from 05_query_pts, random rotation augmentation
     of patch / sub-sample / query like the reference's dataset does when reconstruction is False."""
     q = torch.from_numpy(np.ascontiguousarray(query_pts, dtype=np.float32)).to(dev)
-    _, patch, radius = ops.knn_patch(pts_dev, q, train_opt.points_per_patch)
+    patch_radius = float(getattr(train_opt, 'patch_radius', 0.0))
+    if patch_radius > 0.0:       # radius ablations: ball query, fixed-radius normalisation, |d| not rescaled (eval.py:364-368)
+        _, patch, _, _ = ops.ball_patch(pts_dev, q, train_opt.points_per_patch, patch_radius, eval_opt.seed)
+        radius = None
+    else:
+        _, patch, radius = ops.knn_patch(pts_dev, q, train_opt.points_per_patch)
     uniform = bool(getattr(train_opt, 'uniform_subsample', 0))
     sub = ops.gather_points(pts_dev, ops.subsample(pts_dev, q, train_opt.sub_sample_size, uniform, eval_opt.seed))
     R = torch.from_numpy(_random_rotations(np.random.RandomState(eval_opt.seed), q.shape[0])).to(dev)
@@ -179,7 +182,8 @@ def points_to_surf_eval(eval_opt):
             pts_dev = torch.from_numpy(pts).to(dev)
             if eval_opt.reconstruction:
                 lin, sdf = eng.reconstruct(pts_dev, eval_opt.query_grid_resolution, eval_opt.epsilon, uniform,
-                                           eval_opt.seed, batch=eval_opt.batchSize)
+                                           eval_opt.seed, batch=eval_opt.batchSize,
+                                           patch_radius=float(getattr(train_opt, 'patch_radius', 0.0)))
                 query_pts = ops.query_points(lin, eval_opt.query_grid_resolution).cpu().numpy()
             else:
                 query_pts = np.load(os.path.join(eval_opt.indir, '05_query_pts', name + '.ply.npy')).astype(np.float32)

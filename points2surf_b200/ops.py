@@ -115,13 +115,15 @@ class Engine:
         return out
 
     # ---- fused a1..a9 ----
-    def reconstruct(self, pts, res, eps, uniform_subsample, seed, first_query=0, num_queries=-1, batch=0, cap=None):
+    def reconstruct(self, pts, res, eps, uniform_subsample, seed, first_query=0, num_queries=-1, batch=0, cap=None,
+                    patch_radius=0.0):
+        """patch_radius > 0: ball-query patches of that radius and un-scaled magnitudes (train_opt.patch_radius)."""
         pts = _dev(pts, torch.float32, 'pts')
         N = pts.shape[0]
         if cap is None:
             cap = query_grid(pts, res, eps).numel() if num_queries < 0 else num_queries
         rc = ReconConfig(int(res), int(eps), _lib.SUBSAMPLE_UNIFORM if uniform_subsample else _lib.SUBSAMPLE_WEIGHTED,
-                         int(batch), int(seed) & (2**64 - 1))
+                         int(batch), int(seed) & (2**64 - 1), float(patch_radius), 0)
         lin = torch.empty((max(cap, 1),), dtype=torch.int32, device=pts.device)
         sdf = torch.empty((max(cap, 1),), dtype=torch.float32, device=pts.device)
         Q = C.c_int64()
@@ -130,10 +132,11 @@ class Engine:
                                                _ptr(lin), _ptr(sdf), int(cap), C.byref(Q), _stream()))
         return lin[:Q.value], sdf[:Q.value]
 
-    def reconstruct_host(self, pts_np, res, eps, uniform_subsample, seed, cap, batch=0, out_lin=None, out_sdf=None):
+    def reconstruct_host(self, pts_np, res, eps, uniform_subsample, seed, cap, batch=0, out_lin=None, out_sdf=None,
+                         patch_radius=0.0):
         pts_np = np.ascontiguousarray(pts_np, dtype=np.float32)
         rc = ReconConfig(int(res), int(eps), _lib.SUBSAMPLE_UNIFORM if uniform_subsample else _lib.SUBSAMPLE_WEIGHTED,
-                         int(batch), int(seed) & (2**64 - 1))
+                         int(batch), int(seed) & (2**64 - 1), float(patch_radius), 0)
         lin = out_lin if out_lin is not None else np.empty((cap,), dtype=np.int32)
         sdf = out_sdf if out_sdf is not None else np.empty((cap,), dtype=np.float32)
         Q = C.c_int64()
@@ -152,11 +155,12 @@ def launch_count(reset=False):
 
 
 def sdf_from_logits(logits, patch_radius):
+    """patch_radius None = fixed-radius patches: the magnitude is not rescaled (points_to_surf_eval.py:364-368)."""
     lg = _dev(logits, torch.float32, 'logits')
-    r = _dev(patch_radius, torch.float32, 'patch_radius')
+    r = _dev(patch_radius, torch.float32, 'patch_radius') if patch_radius is not None else None
     out = torch.empty((lg.shape[0],), dtype=torch.float32, device=lg.device)
     with torch.cuda.device(lg.device):
-        check(_lib.load().p2s_sdf_from_logits_dev(_ptr(lg), _ptr(r), lg.shape[0], _ptr(out), _stream()))
+        check(_lib.load().p2s_sdf_from_logits_dev(_ptr(lg), _ptr(r) if r is not None else None, lg.shape[0], _ptr(out), _stream()))
     return out
 
 
@@ -191,6 +195,22 @@ def knn_patch(pts, query_pts, k):
         check(_lib.load().p2s_knn_patch_dev(_ptr(pts), pts.shape[0], _ptr(q), Q, int(k), _ptr(ids), _ptr(patch),
                                             _ptr(radius), _stream()))
     return ids, patch, radius
+
+
+def ball_patch(pts, query_pts, k, patch_radius, seed, query_index_base=0):
+    """Ball-query patches (source/base/point_cloud.py:176-192 + data_loader.py:340-350)
+    -> (ids [Q,k] (pads 0), patch_pts_ps [Q,k,3] (pads at the origin), radius [Q] = patch_radius, in-ball counts [Q])."""
+    pts = _dev(pts, torch.float32, 'pts')
+    q = _dev(query_pts, torch.float32, 'query_pts')
+    Q = q.shape[0]
+    ids = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
+    patch = torch.empty((Q, k, 3), dtype=torch.float32, device=pts.device)
+    radius = torch.empty((Q,), dtype=torch.float32, device=pts.device)
+    counts = torch.empty((Q,), dtype=torch.int32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        check(_lib.load().p2s_ball_patch_dev(_ptr(pts), pts.shape[0], _ptr(q), Q, int(query_index_base), int(k), float(patch_radius),
+                                             int(seed) & (2**64 - 1), _ptr(ids), _ptr(patch), _ptr(radius), _ptr(counts), _stream()))
+    return ids, patch, radius, counts
 
 
 def subsample(pts, query_pts, S, uniform, seed, query_index_base=0):

@@ -42,7 +42,7 @@ def parse_arguments(args=None):
     p.add_argument('--debug_interval', type=int, default='1', help='print logging info each n epochs')
     p.add_argument('--refine', type=str, default='', help='refine model at this path')
     p.add_argument('--gpu_idx', type=int, default=[0], nargs='+', help='GPU indices (this implementation needs >= 0)')
-    p.add_argument('--patch_radius', type=float, default=0.05, help='r <= 0.0 for k-NN queries (the supported mode)')
+    p.add_argument('--patch_radius', type=float, default=0.05, help='Neighborhood of points that is queried per patch. Fixed radius ball query if r > 0.0, k-NN query if r <= 0.0')
     p.add_argument('--net_size', type=int, default=1024, help='number of neurons in the largest fully connected layer')
     p.add_argument('--nepoch', type=int, default=2, help='number of epochs to train for')
     p.add_argument('--batchSize', type=int, default=2, help='input batch size')
@@ -97,8 +97,6 @@ def _check_supported(opt):
             raise ValueError('Unknown output: %s' % o)
     if 'imp_surf' in outs or 'imp_surf_magnitude' not in outs or 'imp_surf_sign' not in outs:
         raise ValueError('Unsupported outputs %s: need imp_surf_magnitude + imp_surf_sign (no imp_surf regression)' % outs)
-    if opt.patch_radius > 0.0:
-        raise ValueError('Unsupported option: fixed-radius patches (patch_radius > 0); use --patch_radius 0 for k-NN patches')
     if opt.sym_op != 'max':
         raise ValueError('Unsupported symmetric operation: %s' % opt.sym_op)
     if opt.single_transformer:
@@ -155,10 +153,11 @@ class GpuAssembler:
     """kNN patch + radius + patch-space normalisation and the global sub-sample of a group of query points of one shape,
     on the device (the call sequence of points2surf_b200.eval._eval_given_queries)."""
 
-    def __init__(self, device, points_per_patch, sub_sample_size, uniform_subsample, seed):
+    def __init__(self, device, points_per_patch, sub_sample_size, uniform_subsample, seed, patch_radius=0.0):
         from . import ops
         self.ops, self.device = ops, device
         self.P, self.S, self.uniform, self.seed = points_per_patch, sub_sample_size, bool(uniform_subsample), int(seed)
+        self.patch_radius = float(patch_radius)          # > 0: ball-query patches of a fixed radius (radius ablations)
         self._clouds = {}
         self.calls = 0
 
@@ -173,8 +172,11 @@ class GpuAssembler:
         """-> patch [n,P,3] (patch space), radius [n], sub-sample [n,S,3] (model space), query [n,3] device tensors."""
         pts_dev = self.cloud(key, pts)
         q = torch.from_numpy(np.ascontiguousarray(query_pts, dtype=np.float32)).to(self.device)
-        _, patch, radius = self.ops.knn_patch(pts_dev, q, self.P)
         self.calls += 1
+        if self.patch_radius > 0.0:
+            _, patch, radius, _ = self.ops.ball_patch(pts_dev, q, self.P, self.patch_radius, self.seed + self.calls)
+        else:
+            _, patch, radius = self.ops.knn_patch(pts_dev, q, self.P)
         ids = self.ops.subsample(pts_dev, q, self.S, self.uniform, self.seed + self.calls)   # a fresh Philox stream per call
         return patch, radius, self.ops.gather_points(pts_dev, ids), q
 
@@ -342,9 +344,10 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
     ts = TrainStep({k: v.to(device) for k, v in state.items()}, opt.use_point_stn, opt.shared_transformer,
                    points_per_patch=opt.points_per_patch, sub_sample_size=opt.sub_sample_size, net_size=opt.net_size, lr=opt.lr,
                    momentum=opt.momentum, device=device, prims=prims, outputs=tuple(output_names),
-                   output_loss_weights=output_loss_weights, fixed_radius=False, dtype=dtype)
+                   output_loss_weights=output_loss_weights, fixed_radius=opt.patch_radius > 0.0, dtype=dtype)
     if assembler is None:
-        assembler = GpuAssembler(device, opt.points_per_patch, opt.sub_sample_size, opt.uniform_subsample, opt.seed + rank)
+        assembler = GpuAssembler(device, opt.points_per_patch, opt.sub_sample_size, opt.uniform_subsample, opt.seed + rank,
+                                 patch_radius=opt.patch_radius)
     rng_aug = np.random.RandomState(opt.seed + rank)            # augmentation / sub-sample streams differ per rank
 
     if is_main:
@@ -371,7 +374,7 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
             ts.lr = lr
             losses = ts.step(batch)                                   # train(): zero_grad, forward, loss, backward, SGD
             train_fraction_done = (train_batchind + 1) / len(train_batches)
-            metrics = calc_metrics(ts.last_logits, batch)
+            metrics = calc_metrics(ts.last_logits, batch, fixed_radius=opt.patch_radius > 0.0)
             _log_line(opt, epoch, train_batchind, len(train_batches), green('train'), losses, metrics)
             step = (epoch + train_fraction_done) * len(train_batches) * opt.batchSize
             if writer is not None:
@@ -381,7 +384,7 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
                 test_batchind += 1
                 tb = _assemble_batch(test_set, test_batches[test_batchind], assembler, rng_aug, device, dtype)
                 pred, tl = ts.evaluate(tb)                            # eval(): running statistics, no gradients
-                tm = calc_metrics(pred, tb)
+                tm = calc_metrics(pred, tb, fixed_radius=opt.patch_radius > 0.0)
                 test_fraction_done = (test_batchind + 1) / len(test_batches)
                 _log_line(opt, epoch, test_batchind, len(train_batches), blue('test'), tl, tm)
                 if writer is not None:

@@ -1,7 +1,7 @@
 """Generate the end-to-end fixtures (tests/golden/e2e_*.npz, points2surf_b200/fitted_fc4.npz).
 
 Run in the build container only (uses /root/reference for config 1):
-    python tests/golden/make_e2e_golden.py [fit] [e2e64] [e2e128] [config1]
+    python tests/golden/make_e2e_golden.py [fit] [e2e64] [e2e128] [config1] [states]
 
 1. `fit`: a rand-init checkpoint gives a shape-unaware SDF, so a reconstructed "mesh" is noise.  To make the
    end-to-end tests (and the bench's mesh stage) reconstruct a surface, the LAST layer (fc4: 2 x 128 + 2) of the
@@ -120,7 +120,7 @@ def config1():
     ref_shims.install()
     from source import data_loader as ref_dl
     from source.points_to_surf_model import PointsToSurfModel
-    src = '/root/reference/datasets/abc_minimal/04_pts/00011084_fddd53ce45f640f3ab922328_trimesh_019.xyz.npy'
+    src = '/root/reference/datasets/abc_minimal/04_pts/00994122_57d9d4755722f9d2d7436f0a_trimesh_000.xyz.npy'   # the shape of abc_minimal/testset.txt
     cloud = np.ascontiguousarray(np.load(src).astype(np.float32)[:, :3])
     res, eps, k, S, seed = 32, 3, 300, 1000, 40938661
     variant = 'vanilla'
@@ -165,8 +165,43 @@ def config1():
                         ids_checksum=np.array(ids_checksum(ids), dtype=np.uint64), ids_head=ids[:2].copy())
 
 
+RNG_CHUNK = 1024
+
+
+def add_rng_states():
+    """Post-process every e2e_*.npz: replay the sequential RandomState sub-sample stream (no network) and store the
+    generator state at every RNG_CHUNK-th query, so that the tests can regenerate the ids chunk-parallel."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(HERE, 'e2e_*.npz'))):
+        g = dict(np.load(path))
+        if 'rng_keys' in g:
+            continue
+        if 'cloud' in g:
+            cloud, variant = g['cloud'], 'vanilla'
+        else:
+            cloud = synth.make_cloud('sphere', int(g['points']), seed=int(g['cloud_seed']))
+            variant = os.path.basename(path).split('_')[1]
+        uniform = bool(synth.VARIANTS[variant]['uniform_subsample'])
+        qpts = orc.query_grid(cloud, int(g['res']), int(g['eps']))
+        rng = np.random.RandomState(int(g['seed']))
+        keys, pos = [], []
+        ids = np.empty((len(qpts), 1000), np.int32)
+        for i in range(len(qpts)):
+            if i % RNG_CHUNK == 0:
+                st = rng.get_state()
+                assert st[0] == 'MT19937' and st[3] == 0
+                keys.append(st[1].copy()); pos.append(st[2])
+            ids[i] = orc.sub_sample_ids(1000, cloud, qpts[i], rng, uniform=uniform)
+        assert ids_checksum(ids) == int(g['ids_checksum']), path
+        g['rng_keys'] = np.stack(keys).astype(np.uint32)
+        g['rng_pos'] = np.array(pos, dtype=np.int32)
+        g['rng_chunk'] = np.array(RNG_CHUNK)
+        np.savez_compressed(path, **g)
+        print('rng states added to', os.path.basename(path), len(keys), 'chunks')
+
+
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['fit', 'e2e64', 'config1', 'e2e128']
+    what = sys.argv[1:] or ['fit', 'e2e64', 'config1', 'e2e128', 'states']
     torch.set_num_threads(int(os.environ.get('P2S_GOLDEN_THREADS', '6')))
     for w in what:
         if w == 'fit':
@@ -177,5 +212,7 @@ if __name__ == '__main__':
             e2e(128, ['vanilla'])
         elif w == 'config1':
             config1()
+        elif w == 'states':
+            add_rng_states()
         else:
             raise SystemExit('unknown step ' + w)

@@ -132,6 +132,49 @@ def gen_assembly():
     np.savez_compressed(os.path.join(HERE, 'assembly.npz'), **out)
 
 
+def gen_ball():
+    """Ball-query patches (radius ablations) through the UNMODIFIED reference dataset (patch_radius > 0), compared with
+    orc.ball_patch in the same run.  Cloud = the 6 000-point abc_minimal subset of assembly.npz."""
+    cloud = np.load(os.path.join(HERE, 'assembly.npz'))['cloud']
+    res, eps, S, seed = 32, 3, 1000, 40938661
+    out = dict(res=res, eps=eps, seed=seed)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, '04_pts'))
+        np.save(os.path.join(d, '04_pts', 'shape.xyz.npy'), cloud)
+        with open(os.path.join(d, 'testset.txt'), 'w') as f:
+            f.write('shape\n')
+        for tag, radius, P in (('small', 0.05, 10), ('large', 0.2, 300)):
+            ds = ref_dl.PointcloudPatchDataset(
+                root=d, shape_list_filename='testset.txt', points_per_patch=P, patch_radius=radius,
+                patch_features=['imp_surf_magnitude', 'imp_surf_sign', 'patch_pts_ids', 'p_index'],
+                epsilon=eps, seed=seed, center='mean', cache_capacity=5, pre_processed_patches=True,
+                query_grid_resolution=res, sub_sample_size=S, reconstruction=True,
+                uniform_subsample=1, fixed_subsample=0, num_workers=0)
+            Q = len(ds)
+            qpts = ds.shape_cache.get(0).imp_surf_query_point_ms
+            kd = orc.make_kdtree(cloud)
+            rng_o = np.random.RandomState(seed)
+            sel = np.linspace(0, Q - 1, 24).astype(np.int64)
+            counts, patches, radii = [], [], []
+            for qi in sel:                      # the dataset rng is consumed in call order: same order on both sides
+                it = ds[int(qi)]
+                oid, ops_, cnt = orc.ball_patch(cloud, kd, qpts[qi], radius, P, rng_o)
+                assert np.array_equal(it['patch_pts_ps'].numpy(), ops_), (tag, qi)
+                assert np.float32(it['patch_radius_ms'].numpy()) == np.float32(radius)
+                counts.append(cnt); patches.append(ops_); radii.append(np.float32(it['patch_radius_ms'].numpy()))
+            counts = np.array(counts)
+            print('ball', tag, 'radius', radius, 'P', P, 'in-ball counts', counts.min(), '..', counts.max(),
+                  'padded', int((counts < P).sum()), 'sub-set', int((counts > P).sum()))
+            assert (counts < P).any() and (counts > P).any() or tag == 'large'
+            out[tag + '_radius'] = radius
+            out[tag + '_P'] = P
+            out[tag + '_query_sel'] = sel
+            out[tag + '_counts'] = counts
+            out[tag + '_patch_ps'] = np.stack(patches)
+    np.savez_compressed(os.path.join(HERE, 'ball.npz'), **out)
+    print('ball.npz written: oracle == reference')
+
+
 def gen_volume():
     out = {}
     for name, res, noise in (('sphere', 32, 0.0), ('noisy', 40, 0.15)):

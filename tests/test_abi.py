@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), 'missing export: ' + s
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.p2s_abi_version() == 1
+    assert lib.p2s_abi_version() == 2
 
 
 @pytest.mark.parametrize('variant', ['vanilla', 'max', 'uniform'])

@@ -93,10 +93,24 @@ def test_model_module_is_a_drop_in():
         PointsToSurfModel(single_transformer=True, output_dim=2)
 
 
+def test_radius_ablation_checkpoint_reconstructs(tmp_path):
+    """train_opt.patch_radius > 0 (experiments/train_p2s_*_radius.sh): ball-query patches through the eval entry point."""
+    root, models, _ = _make_dataset(tmp_path)
+    opt_ns = synth.make_train_opt('vanilla')
+    opt_ns.patch_radius = 0.2
+    torch.save(opt_ns, models / 'p2s_test_params.pth')
+    opt = p2s_eval.parse_arguments(['--indir', str(root), '--outdir', str(tmp_path / 'r'), '--modeldir', str(models), '--models', 'p2s_test',
+                                    '--query_grid_resolution', '16', '--epsilon', '3'])
+    opt.reconstruction = True
+    p2s_eval.points_to_surf_eval(opt)
+    d = np.load(tmp_path / 'r' / 'rec' / 'dist_ms' / 'shape_a.xyz.npy')
+    assert np.isfinite(d).all() and np.abs(d).max() <= 1.0        # tanh^2, not rescaled by a radius (eval.py:364-368)
+
+
 def test_unsupported_options_raise(tmp_path):
     root, models, _ = _make_dataset(tmp_path)
     opt_ns = synth.make_train_opt('vanilla')
-    opt_ns.patch_radius = 0.1
+    opt_ns.sym_op = 'sum'
     torch.save(opt_ns, models / 'p2s_test_params.pth')
     opt = p2s_eval.parse_arguments(['--indir', str(root), '--outdir', str(tmp_path / 'r'), '--modeldir', str(models), '--models', 'p2s_test',
                                     '--query_grid_resolution', '16', '--epsilon', '3'])

@@ -18,6 +18,8 @@ Stated bars
     independent sampling of itself) + 0.05 voxel;
   * every engine vertex within 0.5 voxel of an oracle-mesh vertex.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -36,11 +38,29 @@ def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
 
+_IDS = {}
+
+
+def _ids_chunk(c):
+    """Ids of queries [c*chunk, (c+1)*chunk): the sequential stream resumed from the stored generator state."""
+    a = _IDS
+    rng = np.random.RandomState()
+    rng.set_state(('MT19937', a['keys'][c], int(a['pos'][c]), 0, 0.0))
+    lo, hi = c * a['chunk'], min(len(a['qpts']), (c + 1) * a['chunk'])
+    return np.stack([orc.sub_sample_ids(1000, a['cloud'], a['qpts'][i], rng, uniform=a['uniform']) for i in range(lo, hi)]).astype(np.int32)
+
+
 def reference_sub_ids(cloud, qpts, seed, uniform, g):
-    rng = np.random.RandomState(seed)
-    ids = np.empty((len(qpts), 1000), np.int32)
-    for i in range(len(qpts)):
-        ids[i] = orc.sub_sample_ids(1000, cloud, qpts[i], rng, uniform=uniform)
+    """The reference's sub-sample ids of every query: one RandomState(seed) stream consumed query after query
+    (source/data_loader.py:272-277,358-362).  Regenerated chunk-parallel from the generator states stored with the
+    fixture (the stream itself is sequential) and verified against the fixture's checksum."""
+    import multiprocessing as mp
+    assert int(g['rng_pos'][0]) == 624 and np.array_equal(g['rng_keys'][0], np.random.RandomState(seed).get_state()[1])
+    _IDS.update(keys=g['rng_keys'], pos=g['rng_pos'], chunk=int(g['rng_chunk']), qpts=qpts, cloud=cloud, uniform=uniform)
+    n = len(g['rng_pos'])
+    workers = max(1, min(n, (os.cpu_count() or 2) - 1, 32))
+    with mp.get_context('fork').Pool(workers) as pool:
+        ids = np.concatenate(pool.map(_ids_chunk, range(n)))
     if not np.array_equal(ids[:2], g['ids_head']) or ids_checksum(ids) != int(g['ids_checksum']):
         pytest.fail('the regenerated RandomState sub-sample ids differ from the ones the fixture was computed with '
                     '(NumPy float32 reduction order differs on this host?) -- regenerate tests/golden/e2e_*.npz')

@@ -420,4 +420,38 @@ def test_other_patch_and_subsample_sizes(variant, P, S):
         rid = orc.knn_bruteforce(cloud, q[i].astype(np.float32), P)
         assert np.array_equal(ids[i].cpu().numpy(), np.asarray(rid[0] if isinstance(rid, tuple) else rid).astype(np.int32))
     with pytest.raises(ops.P2SError):
-        ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=1200, sub_sample_size=S)   # large_kNN: documented limit 512
+        ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=2000, sub_sample_size=S)   # documented limit 1536
+
+
+def test_large_knn_1200_point_patches():
+    """experiments/train_p2s_large_kNN.sh: points_per_patch 1200 (per-branch QSTN topology) on all three network paths and
+    through the kNN kernel's 2048-candidate instantiation."""
+    variant, P, S = 'uniform', 1200, 1000
+    v = synth.VARIANTS[variant]
+    sd = synth.make_state_dict(variant, seed=81)
+    inp = synth.make_model_inputs(12, points_per_patch=P, sub_sample_size=S, seed=82)
+    ref = orc.model_forward(sd, inp['patch_pts_ps'], inp['pts_sub_sample_ms'], inp['imp_surf_query_point_ms'],
+                            v['use_point_stn'], v['shared_transformer'])
+    args = (cu(inp['patch_pts_ps']), cu(inp['pts_sub_sample_ms']), cu(inp['imp_surf_query_point_ms']))
+    scale = max(1.0, np.abs(ref).max())
+    e32 = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=P, sub_sample_size=S, precision='fp32')
+    assert np.abs(e32.forward(*args).cpu().numpy() - ref).max() < 2e-3 * scale
+    etc = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], points_per_patch=P, sub_sample_size=S, precision='tc', guard_band=0.0)
+    assert np.abs(etc.forward(*args).cpu().numpy() - ref).max() < 3e-2 * scale
+    etc.set_precision('tc', guard_band=1e9)
+    assert np.abs(etc.forward(*args).cpu().numpy() - ref).max() < 2e-3 * scale
+    cloud = synth.make_cloud('torus', 6000, seed=83)
+    q = orc.query_grid(cloud, 24, 3)[::37][:48]
+    ids, patch, radius = ops.knn_patch(cu(cloud), cu(q), P)
+    ids, patch, radius = ids.cpu().numpy(), patch.cpu().numpy(), radius.cpu().numpy()
+    kd = orc.make_kdtree(cloud)
+    for i in range(len(q)):
+        oid, ops_, orad = orc.knn_patch(cloud, kd, q[i], P)
+        bid, d2 = orc.knn_bruteforce(cloud, q[i], P)
+        gd = ((cloud[ids[i]].astype(np.float64) - q[i].astype(np.float64)) ** 2).sum(1)
+        assert np.array_equal(gd, d2) and radius[i] == orad
+        if np.all(np.diff(d2) > 0):
+            assert np.array_equal(ids[i], oid) and np.array_equal(patch[i], ops_)
+    # fused pipeline at this patch size
+    lin, sdf = etc.reconstruct(cu(cloud), 16, 3, 1, 5)
+    assert torch.isfinite(sdf).all() and lin.numel() == len(orc.query_grid(cloud, 16, 3))

@@ -120,3 +120,18 @@ def test_train_oracle_reproduces_reference_iteration(variant):
     out = train_oracle.train_iteration(sd, train_fixture_batch(variant), v['use_point_stn'], v['shared_transformer'],
                                        lr=0.01, momentum=0.9)
     check_train_digest(variant, out['grads'], out['new_state'], out['losses'], out['logits'].numpy(), tol=2e-2)
+
+
+def test_ball_patch_oracle_matches_reference_golden():
+    """orc.ball_patch against tests/golden/ball.npz (made by the unmodified reference dataset with patch_radius > 0)."""
+    g = load_golden('ball.npz')
+    cloud = load_golden('assembly.npz')['cloud']
+    kd = orc.make_kdtree(cloud)
+    qall = orc.query_grid(cloud, int(g['res']), int(g['eps']))
+    for tag in ('small', 'large'):
+        rng = np.random.RandomState(int(g['seed']))
+        radius, P = float(g[tag + '_radius']), int(g[tag + '_P'])
+        for j, qi in enumerate(g[tag + '_query_sel']):
+            ids, patch, cnt = orc.ball_patch(cloud, kd, qall[qi], radius, P, rng)
+            assert cnt == int(g[tag + '_counts'][j])
+            assert np.array_equal(patch, g[tag + '_patch_ps'][j])

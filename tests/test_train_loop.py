@@ -104,7 +104,8 @@ def test_two_epochs_end_to_end(tmp_path, capsys, order):
 def test_unsupported_training_options_raise():
     base = ['--outputs', 'imp_surf_magnitude', 'imp_surf_sign', '--patch_radius', '0.0']
     p2s_train._check_supported(p2s_train.parse_arguments(base))
-    for extra in (['--patch_radius', '0.1'], ['--sym_op', 'sum'], ['--single_transformer', '1'], ['--training_order', 'bogus'],
+    p2s_train._check_supported(p2s_train.parse_arguments(base + ['--patch_radius', '0.1']))     # radius ablations: ball-query patches
+    for extra in (['--sym_op', 'sum'], ['--single_transformer', '1'], ['--training_order', 'bogus'],
                   ['--fixed_subsample', '1'], ['--outputs', 'imp_surf'], ['--outputs', 'normals']):
         with pytest.raises(ValueError):
             p2s_train._check_supported(p2s_train.parse_arguments(base + extra))
