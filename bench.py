@@ -49,6 +49,10 @@ def parse():
     ap.add_argument('--mix_shapes', action='store_true', help='sphere / torus / box per rank instead of same-size spheres')
     ap.add_argument('--cpu_sample', type=int, default=256, help='queries in the bounded CPU-baseline sample')
     ap.add_argument('--seed', type=int, default=40938661)
+    ap.add_argument('--workload', default='headline', choices=['headline', 'sharded'],
+                    help="'sharded': only the shape-sharded job (configs 3 / 5: --model, --shapes_per_gpu, --grid_res), shapes/s")
+    ap.add_argument('--shapes_per_gpu', type=int, default=2)
+    ap.add_argument('--skip_sharded', action='store_true', help='headline run without the sharded-job / tile-sharded sections')
     return ap.parse_args()
 
 
@@ -223,6 +227,94 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.samples)}
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# Sharded jobs, each timed end to end on the device: CUDA events around the rank's own work
+# including the final gather, barrier on both sides, max over ranks.
+# ----------------------------------------------------------------------------------------------------
+def _timed_region(fn, dev, world, dist):
+    import torch
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), out
+
+
+def run_sharded_job(model, shapes_per_gpu, res, eps, seed, points, precision, guard, rank, world, dev, dist):
+    """Shape-level sharding (BASELINE configs 3 and 5): shapes_per_gpu * world synthetic shapes (sphere / torus / box mix),
+    greedy LPT assignment by the candidate-query count of the grid kernel, every rank runs the WHOLE pipeline for its shapes
+    (queries -> SDF band -> sign propagation -> marching cubes), meshes gathered to rank 0 point-to-point.  The checkpoint
+    has the fitted last layer so that a surface is meshed."""
+    import torch
+    from points2surf_b200 import ops, synth, sharding
+    v = synth.VARIANTS[model]
+    kinds = ['sphere', 'torus', 'box']
+    n_shapes = shapes_per_gpu * world
+    clouds = [torch.from_numpy(synth.make_cloud(kinds[i % 3], points, seed=i)).to(dev) for i in range(n_shapes)]
+    loads = [int(ops.query_grid(c, res, eps).numel()) for c in clouds]          # every rank computes the same table
+    bins, tot = sharding.lpt_assign(loads, world)
+    mine = bins[rank]
+    sd = synth.make_state_dict(model, 6 if model == 'vanilla' else 4, fitted=True)
+    eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=dev.index, precision=precision, guard_band=guard)
+
+    def one(i):
+        lin, sdf = eng.reconstruct(clouds[i], res, eps, v['uniform_subsample'], seed, cap=loads[i])
+        vol, _ = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
+        mv, mf = ops.marching_cubes(vol, 0.0)
+        return (i, mv, mf)
+
+    def job():
+        meshes = [one(i) for i in mine]
+        return sharding.gather_meshes(meshes, dst=0)
+
+    if mine:
+        one(mine[0])                                   # warm-up: workspaces, NCCL channels
+    job()
+    ms, got = _timed_region(job, dev, world, dist)
+    eng.close()
+    res_d = {'workload': '%d shapes (%d per GPU; sphere / torus / box, %d points each), %s model with fitted last layer, grid_res %d, '
+                         'epsilon %d: queries -> SDF band -> sign propagation -> marching cubes -> meshes gathered on rank 0; '
+                         'LPT assignment by candidate-query count' % (n_shapes, shapes_per_gpu, points, model, res, eps),
+             'shapes': n_shapes, 'ms': ms, 'shapes_per_s': n_shapes / (ms * 1e-3), 'queries': int(sum(loads)),
+             'queries_per_s': sum(loads) / (ms * 1e-3), 'lpt_max_over_mean_load': max(tot) / (sum(tot) / world)}
+    if rank == 0:
+        res_d['meshes_on_rank0'] = len(got)
+        res_d['mesh_bytes'] = int(sum(m[1].numel() * 4 + m[2].numel() * 4 for m in got))
+        res_d['faces_total'] = int(sum(m[2].shape[0] for m in got))
+    return res_d
+
+
+def run_tile_sharded(eng, pts, res, eps, uniform, seed, Q, rank, world, dev, dist):
+    """Tile-level sharding of ONE shape (strong scaling): rank r reconstructs a contiguous slab of the ordered query list,
+    the SDF band is gathered point-to-point on rank 0, which runs sign propagation and marching cubes."""
+    from points2surf_b200 import ops, sharding
+    first, count = sharding.query_slab(Q, rank, world)
+    counts = [sharding.query_slab(Q, r, world)[1] for r in range(world)]
+
+    def job():
+        lin, sdf = eng.reconstruct(pts, res, eps, uniform, seed, first_query=first, num_queries=count)
+        band = sharding.gather_band(sdf, counts, dst=0) if world > 1 else sdf
+        if rank == 0:
+            lin_all = ops.query_grid(pts, res, eps) if world > 1 else lin
+            vol, _ = ops.sdf_to_volume(lin_all, band, res, 5, 13.0)
+            return ops.marching_cubes(vol, 0.0)
+        return None
+
+    job()
+    ms, out = _timed_region(job, dev, world, dist)
+    return {'workload': 'one shape, ordered query list cut into %d contiguous slabs, band gathered on rank 0 which meshes it' % world,
+            'queries': int(Q), 'ms': ms, 'queries_per_s': Q / (ms * 1e-3), 'shapes_per_s': 1e3 / ms,
+            'faces': int(out[1].shape[0]) if out is not None else None}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -241,6 +333,24 @@ def run_b200(args):
     if precision == 'auto':
         precision = 'tc'
     guard = args.guard_band if args.guard_band is not None else (0.05 if precision == 'tc' else 0.0)
+    if args.workload == 'sharded':
+        # BASELINE configs 3 / 5 on their own: e.g. --model max --grid_res 256 --shapes_per_gpu 1 (config 3 at --gpus 8),
+        # --model vanilla --grid_res 512 --shapes_per_gpu 8 (config 5 at --gpus 8).  Metric: shapes/s reconstructed.
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        job = run_sharded_job(args.model, args.shapes_per_gpu, args.grid_res, args.epsilon, args.seed, args.points, precision, guard,
+                              rank, world, dev, dist)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        if rank == 0:
+            print(json.dumps({'metric': 'shapes/sec reconstructed at grid_res=%d (marching cubes and mesh gather included)' % args.grid_res,
+                              'value': job['shapes_per_s'], 'unit': 'shapes/s', 'n_gpus': world, 'steps': 1, 'warmup': 1,
+                              'ms_per_step': job['ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                              'dtype': 'f16 operands / f32 accumulate (tcgen05)', 'data': 'synthetic', 'config': {'workload': job['workload']},
+                              'clocks': sampler.summary(), 'sharded_job': job}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     fc4_bias = calibrate_output_bias(sd, args.model, local_rank)
     eng = ops.Engine(sd, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
@@ -353,6 +463,17 @@ def run_b200(args):
                       'shapes_per_s_incl_mesh': world * 1e3 / (dev_ms / args.steps + float(tt[0].item()) + float(tt[1].item()))}
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    sharded_job = tile_sharded = None
+    if not args.skip_sharded:
+        # config 3 analogue (max model, mixed shapes, LPT, whole pipeline + mesh gather timed) and strong scaling of one shape
+        sharded_job = run_sharded_job('max', args.shapes_per_gpu, args.grid_res, args.epsilon, args.seed, args.points, precision, guard,
+                                      rank, world, dev, dist)
+        sd_fit = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4, fitted=True)
+        eng_fit = ops.Engine(sd_fit, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
+        pts0 = torch.from_numpy(synth.make_cloud('sphere', args.points, seed=0)).to(dev)     # the same shape on every rank
+        Q0 = int(ops.query_grid(pts0, args.grid_res, args.epsilon).numel())
+        tile_sharded = run_tile_sharded(eng_fit, pts0, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, Q0, rank, world, dev, dist)
+        eng_fit.close()
     e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
     guard_frac = guard_total / max(Q * (args.steps + max(args.warmup, 3)), 1)
 
@@ -400,6 +521,8 @@ def run_b200(args):
                                        % (args.cpu_sample, cpu['workers'], cpu['t_assemble_s'], cpu['threads'], cpu['t_network_s'])},
             'tensor_flops_per_s': value * FLOP_PER_QUERY[args.model],
             'mesh_stage': mesh_stage,
+            'sharded_job': sharded_job,
+            'tile_sharded_one_shape': tile_sharded,
         }
         print(json.dumps(line))
     if world > 1:

@@ -1,7 +1,8 @@
 // K8: marching cubes at `level` + unit-cube transform + orientation fix -- the tail of
 // sdf.implicit_surface_to_mesh (source/sdf.py:211-227).  The reference delegates to
 // skimage.measure.marching_cubes_lewiner and trimesh.repair.fix_inversion (both absent here: parity
-// unpinned, see oracle/mc_oracle.py for the shared conventions).  HBM-bound: res^3*4 B read (+ L2-resident
+// unpinned, see oracle/mc_oracle.py for the shared conventions).  Ambiguous faces are resolved by the asymptotic decider
+// (the face test of Lewiner's algorithm); the interior (tunnel) test of MC33 is not implemented.  HBM-bound: res^3*4 B read (+ L2-resident
 // re-reads of neighbours), ~20 B/voxel of scan scratch, V*12 + F*12 B written.
 //   1. flag sign-changing grid edges (3 per voxel)      2. exclusive scan -> vertex ids (welded by edge)
 //   3. emit vertices (linear interpolation, fp32)       4. per-cell case -> triangle count, scan
@@ -45,14 +46,37 @@ __global__ void mc_emit_verts_kernel(const float* __restrict__ vol, int R, float
         verts[(int64_t)id * 3 + d] = __fmul_rn(__fsub_rn(__fdiv_rn(__fadd_rn(p[d], 0.5f), (float)R), 0.5f), 2.0f);
 }
 
-__device__ __forceinline__ int mc_case(const float* __restrict__ vol, int R, float level, int cx, int cy, int cz) {
+// Table row of a cell: the corner-sign case plus, for every ambiguous face (+-+-), the asymptotic decider -- are the two
+// positive corners joined through the face?  The bilinear interpolant's saddle value is (A*C - B*D) / (A + C - B - D) with
+// A, C / B, D the two diagonals (values minus level); the denominator's sign is that of the A/C diagonal, so the decision is
+// the sign of A*C - B*D, evaluated in float64 with separately rounded products (no FMA contraction) exactly like the CPU
+// restatement (oracle/mc_topo.py), so that both sides take identical decisions.
+__device__ __forceinline__ int mc_row(const float* __restrict__ vol, int R, float level, int cx, int cy, int cz) {
     int c = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
         c |= (vol[((int64_t)(cx + dx) * R + (cy + dy)) * R + (cz + dz)] > level) ? (1 << k) : 0;
     }
-    return c;
+    int row = kMcRowBase[c];
+    const unsigned amb = kMcAmbMask[c];
+    if (amb) {
+        int bit = 0;
+        for (int f = 0; f < 6; ++f) {
+            if (!((amb >> f) & 1u)) continue;
+            double d[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = kMcFaceRing[f][i];
+                d[i] = __dsub_rn((double)vol[((int64_t)(cx + (k & 1)) * R + (cy + ((k >> 1) & 1))) * R + (cz + ((k >> 2) & 1))], (double)level);
+            }
+            const double num = __dsub_rn(__dmul_rn(d[0], d[2]), __dmul_rn(d[1], d[3]));
+            const bool joined = ((c >> kMcFaceRing[f][0]) & 1) ? (num > 0.0) : (num < 0.0);
+            row += joined ? (1 << bit) : 0;
+            ++bit;
+        }
+    }
+    return row;
 }
 
 __global__ void mc_cell_count_kernel(const float* __restrict__ vol, int R, float level, uint8_t* __restrict__ counts) {
@@ -60,7 +84,7 @@ __global__ void mc_cell_count_kernel(const float* __restrict__ vol, int R, float
     const int C = R - 1;
     if (i >= (int64_t)C * C * C) return;
     int cz = (int)(i % C), cy = (int)((i / C) % C), cx = (int)(i / ((int64_t)C * C));
-    counts[i] = kMcTriCount[mc_case(vol, R, level, cx, cy, cz)];
+    counts[i] = kMcTriCount[mc_row(vol, R, level, cx, cy, cz)];
 }
 
 __global__ void mc_emit_faces_kernel(const float* __restrict__ vol, int R, float level, const uint8_t* __restrict__ counts,
@@ -72,7 +96,7 @@ __global__ void mc_emit_faces_kernel(const float* __restrict__ vol, int R, float
     int n = counts[i];
     if (n == 0) return;
     int cz = (int)(i % C), cy = (int)((i / C) % C), cx = (int)(i / ((int64_t)C * C));
-    int cs = mc_case(vol, R, level, cx, cy, cz);
+    int cs = mc_row(vol, R, level, cx, cy, cz);
     int32_t off = offs[i];
     for (int t = 0; t < n; ++t) {
         if (off + t >= fcap) return;

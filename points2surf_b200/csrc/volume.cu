@@ -38,6 +38,7 @@ struct Ctrl {
     int error;                  // 1: iteration cap hit
     unsigned nonzero_seen;      // some sample is not exactly 0 (sdf.py:187-189)
     unsigned bad_index;         // scatter: number of voxel indices outside [0, res^3)
+    unsigned long long visits;  // tile evaluations (diagnostics)
 };
 
 __global__ void any_nonzero_kernel(const float* __restrict__ sdf, int64_t Q, Ctrl* c) {
@@ -106,7 +107,7 @@ struct PropParams {
     uint8_t* flags[2];
     int* voteZeros;
     Ctrl* ctrl;
-    int res, lo, hi, ntx, nty, ntz, maxIters;
+    int res, lo, hi, ntx, nty, ntz, maxIters, words;
     float thr;
 };
 
@@ -115,8 +116,10 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
     extern __shared__ __align__(16) uint8_t smem[];
     const int res = p.res, hl = -p.lo, hh = p.hi, W = hl + hh + 1;
     const int X0 = TX + hl + hh, Y0 = TY + hl + hh, Z0 = TZ + hl + hh;
-    uint8_t* s0 = smem;                                                 // [X0][Y0][Z0] sign bytes (with U0 flag)
-    int8_t* t1 = (int8_t*)(smem + ((X0 * Y0 * Z0 + 15) & ~15));         // [X0][Y0][TZ] z sums (|.| <= 11)
+    const int HW = (max(hl, hh) + 3) >> 2, WPR = TZ / 4 + 2 * HW;     // halo words per side, words per row
+    const int ZS = 4 * WPR, zoff = 4 * HW - hl;                        // row stride in bytes; smem byte zoff <-> z = bz - hl
+    uint8_t* s0 = smem;                                                 // [X0][Y0][ZS] sign bytes (with U0 flag)
+    int8_t* t1 = (int8_t*)(smem + ((X0 * Y0 * ZS + 15) & ~15));         // [X0][Y0][TZ] z sums (|.| <= 11)
     int16_t* t2 = (int16_t*)((uint8_t*)t1 + ((X0 * Y0 * TZ + 15) & ~15));   // [X0][TY][TZ] zy sums (|.| <= 121)
     __shared__ int sh[8];   // 0 dS, 1 voteZeros, 2..7 changed bbox (min x,y,z, max x,y,z)
     const int tid = threadIdx.x;
@@ -143,17 +146,49 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
             const int tz = tile % p.ntz, ty = (tile / p.ntz) % p.nty, tx = tile / (p.ntz * p.nty);
             const int bx = tx * TX, by = ty * TY, bz = tz * TZ;
             if (tid < 8) sh[tid] = tid < 2 ? 0 : (tid < 5 ? 1 << 20 : -1);
-            if (tid == 0) flagCur[tile] = 0;
-            // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration
-            for (int i = tid; i < X0 * Y0 * Z0; i += kPropThreads) {
-                const int z = i % Z0, xy = i / Z0, y = xy % Y0, x = xy / Y0;
-                const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1), gz = min(max(bz + z - hl, 0), res - 1);
-                s0[i] = __ldcg(in + ((size_t)gx * res + gy) * res + gz);
+            if (tid == 0) { flagCur[tile] = 0; atomicAdd(&p.ctrl->visits, 1ull); }
+            // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration, L1 may
+            // hold stale lines.  Rows are fetched as aligned 32-bit words, four independent loads in flight per thread (a byte
+            // per load made the kernel latency-bound at ~0.4 TB/s); resolutions that are not a multiple of 4 take byte loads.
+            if (p.words) {
+                const int total = X0 * Y0 * WPR, zw0 = (bz >> 2) - HW, lastw = (res >> 2) - 1;
+                uint32_t* s0w = reinterpret_cast<uint32_t*>(s0);
+                for (int base = 0; base < total; base += 4 * kPropThreads) {
+                    uint32_t w[4];
+                    int gz[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = base + k * kPropThreads + tid;
+                        w[k] = 0; gz[k] = 0;
+                        if (i < total) {
+                            const int row = i / WPR, wi = i - row * WPR, x = row / Y0, y = row - x * Y0;
+                            const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1);
+                            gz[k] = zw0 + wi;
+                            w[k] = __ldcg(reinterpret_cast<const uint32_t*>(in + ((size_t)gx * res + gy) * res) + min(max(gz[k], 0), lastw));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = base + k * kPropThreads + tid;
+                        if (i < total) {
+                            uint32_t v = w[k];
+                            if (gz[k] < 0) v = (v & 0xffu) * 0x01010101u;            // left of the volume: first voxel of the row
+                            else if (gz[k] > lastw) v = (v >> 24) * 0x01010101u;     // right of it: last voxel
+                            s0w[i] = v;
+                        }
+                    }
+                }
+            } else {
+                for (int i = tid; i < X0 * Y0 * Z0; i += kPropThreads) {
+                    const int z = i % Z0, xy = i / Z0, y = xy % Y0, x = xy / Y0;
+                    const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1), gz = min(max(bz + z - hl, 0), res - 1);
+                    s0[xy * ZS + zoff + z] = __ldcg(in + ((size_t)gx * res + gy) * res + gz);
+                }
             }
             __syncthreads();
             for (int i = tid; i < X0 * Y0 * TZ; i += kPropThreads) {       // sum along z
                 const int z = i & (TZ - 1), xy = i >> 5;
-                const uint8_t* r = s0 + xy * Z0 + z;
+                const uint8_t* r = s0 + xy * ZS + zoff + z;
                 int acc = 0;
                 for (int t = 0; t < W; ++t) acc += sign_of(r[t]);
                 t1[i] = (int8_t)acc;
@@ -186,7 +221,7 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                         int vote = 0;
                         if (!(fabsf((float)acc) < p.thr)) vote = acc > 0 ? 1 : (acc < 0 ? -1 : 0);
                         nz += (vote == 0);
-                        const uint8_t b = s0[((x + hl) * Y0 + (y + hl)) * Z0 + z + hl];
+                        const uint8_t b = s0[((x + hl) * Y0 + (y + hl)) * ZS + zoff + hl + z];
                         uint8_t nb = b;
                         if (b & kU0) {
                             const int so = sign_of(b);
@@ -314,7 +349,10 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     // persistent cooperative launch: as many CTAs as are co-resident (the runtime refuses a larger grid instead of hanging)
     const int hl = -pp.lo, hh = pp.hi;
     const int X0 = TX + hl + hh, Y0 = TY + hl + hh, Z0 = TZ + hl + hh;
-    const size_t smem = (size_t)((X0 * Y0 * Z0 + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
+    const int HW = (std::max(hl, hh) + 3) / 4, ZS = TZ + 8 * HW;
+    (void)Z0;
+    pp.words = (res % 4 == 0) ? 1 : 0;       // aligned 32-bit row loads need word-aligned rows
+    const size_t smem = (size_t)((X0 * Y0 * ZS + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
     int dev_id = 0, sms = 148, per_sm = 0;
     P2S_CUDA(cudaGetDevice(&dev_id));
     P2S_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
@@ -332,6 +370,12 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     P2S_CHECK(h.bad_index == 0, "voxel index outside [0, res^3): query points must lie in [-1, 1)^3 (the reference raises IndexError / wraps)");
     P2S_CHECK(h.error == 0, "sign propagation did not converge");
     if (iterations_host) *iterations_host = h.iters;
+    {
+        static int stats = -1;
+        if (stats < 0) { const char* e = getenv("P2S_VOL_STATS"); stats = (e && e[0] == '1') ? 1 : 0; }
+        if (stats) fprintf(stderr, "p2s sign propagation: res %d, %d iterations, %llu tile evaluations over %d tiles (%.1f per tile; a full sweep per iteration would be %d), grid %u x %d threads, %zu B smem\n",
+                           res, h.iters, h.visits, numTiles, (double)h.visits / numTiles, h.iters + 1, grid, kPropThreads, smem);
+    }
     if (Q > 0 && !h.nonzero_seen) {
         // the reference prints a warning and returns without writing anything (sdf.py:187-189)
         if (iterations_host) *iterations_host = -1;

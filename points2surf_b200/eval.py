@@ -112,6 +112,14 @@ def _random_rotations(rng, n):
     return R.astype(np.float32)
 
 
+def _rotate_inputs(patch, sub, q, R):
+    """trafo.transform_points(x, rand_rot) = (R x^T)^T for the patch, the sub-sample and the query point
+    (data_loader.py:385-393; the reference computes in float64 and casts to float32, here float32 throughout)."""
+    Rt = R.transpose(1, 2)
+    return (torch.matmul(patch, Rt).contiguous(), torch.matmul(sub, Rt).contiguous(),
+            torch.matmul(q.unsqueeze(1), Rt).squeeze(1).contiguous())
+
+
 def _eval_given_queries(eng, train_opt, eval_opt, pts_dev, query_pts, dev):
     """Non-reconstruction pass (full_eval.py:31-41): queries from 05_query_pts, random rotation augmentation
     of patch / sub-sample / query like the reference's dataset does when reconstruction is False."""
@@ -125,9 +133,7 @@ def _eval_given_queries(eng, train_opt, eval_opt, pts_dev, query_pts, dev):
     uniform = bool(getattr(train_opt, 'uniform_subsample', 0))
     sub = ops.gather_points(pts_dev, ops.subsample(pts_dev, q, train_opt.sub_sample_size, uniform, eval_opt.seed))
     R = torch.from_numpy(_random_rotations(np.random.RandomState(eval_opt.seed), q.shape[0])).to(dev)
-    patch = torch.matmul(patch, R.transpose(1, 2)).contiguous()
-    sub = torch.matmul(sub, R.transpose(1, 2)).contiguous()
-    qr = torch.matmul(q.unsqueeze(1), R.transpose(1, 2)).squeeze(1).contiguous()
+    patch, sub, qr = _rotate_inputs(patch, sub, q, R)
     out = []
     bs = eval_opt.batchSize if eval_opt.batchSize > 0 else 4096
     for b0 in range(0, q.shape[0], bs):
@@ -175,8 +181,16 @@ def points_to_surf_eval(eval_opt):
                 seed=eval_opt.seed, sequential_shapes=True, identical_epochs=False)
             list(iter(sampler))
             shape_patch_inds = sampler.shape_patch_inds
+        # shapes are independent: greedy LPT over ranks by the candidate-query count in reconstruction mode (the cheap grid
+        # kernel gives Q before any network work), round-robin otherwise; every rank derives the same table
+        mine = None
+        if world > 1 and eval_opt.reconstruction:
+            from . import sharding
+            loads = [int(ops.query_grid(torch.from_numpy(_load_pts(eval_opt.indir, n)).to(dev), eval_opt.query_grid_resolution,
+                                        eval_opt.epsilon).numel()) for n in names]
+            mine = set(sharding.shapes_for_rank(len(names), rank, world, loads=loads))
         for si, name in enumerate(names):
-            if si % world != rank:
+            if (si not in mine) if mine is not None else (si % world != rank):
                 continue
             pts = _load_pts(eval_opt.indir, name)
             pts_dev = torch.from_numpy(pts).to(dev)

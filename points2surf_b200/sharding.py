@@ -5,8 +5,11 @@ import torch
 import torch.distributed as dist
 
 
-def shapes_for_rank(num_shapes, rank, world):
-    """Round-robin shape assignment used by points2surf_b200.eval."""
+def shapes_for_rank(num_shapes, rank, world, loads=None):
+    """Shape assignment used by points2surf_b200.eval: greedy LPT by `loads` (candidate-query counts) when given,
+    round-robin otherwise."""
+    if loads is not None:
+        return lpt_assign(loads, world)[0][rank]
     return [i for i in range(num_shapes) if i % world == rank]
 
 
@@ -30,12 +33,53 @@ def reduce_timing(ms_local, units_local, device=None):
     return float(t.item()), float(u.item())
 
 
-def gather_band(sdf_slab, counts, device=None):
-    """Tile mode: every rank holds the SDF of its slab; returns the full band on every rank (all_gather of
-    padded slabs).  `counts` = slab sizes of all ranks (from query_slab)."""
+def lpt_assign(loads, world):
+    """Greedy longest-processing-time assignment of independent shapes to ranks: shapes sorted by
+    decreasing load (the candidate-query count Q of the cheap grid kernel), each to the currently least loaded rank.
+    Deterministic (ties by shape index / lowest rank), so every rank computes the same table without communication.
+    -> (list of shape-index lists per rank, per-rank load)."""
+    order = sorted(range(len(loads)), key=lambda i: (-float(loads[i]), i))
+    bins, tot = [[] for _ in range(world)], [0.0] * world
+    for i in order:
+        r = min(range(world), key=lambda k: (tot[k], k))
+        bins[r].append(i)
+        tot[r] += float(loads[i])
+    return [sorted(b) for b in bins], tot
+
+
+def _p2p_gather(tensor, counts_rows, dst):
+    """Rows of `tensor` from every rank to `dst` by point-to-point transfers (NCCL send/recv over NVLink on GPUs, gloo on
+    CPU): only `dst` receives, and only the real bytes move -- no padding, no replication to ranks that do not need it.
+    `counts_rows[r]` = rows held by rank r (known to everyone).  Returns the list of per-rank tensors on dst, [] elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        out, reqs = [], []
+        for r in range(world):
+            if r == dst:
+                out.append(tensor)
+            else:
+                buf = torch.empty((counts_rows[r],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+                out.append(buf)
+                if counts_rows[r] > 0:
+                    reqs.append(dist.irecv(buf, src=r))
+        for q in reqs:
+            q.wait()
+        return out
+    if counts_rows[rank] > 0:
+        dist.send(tensor.contiguous(), dst=dst)
+    return []
+
+
+def gather_band(sdf_slab, counts, dst=None, device=None):
+    """Tile mode: every rank holds the SDF of its slab of one shape's ordered query list.  dst=None: the full band on
+    every rank (one padded all_gather).  dst=r: only rank r -- the one that runs sign propagation and marching cubes --
+    receives it (point-to-point, Q*4 bytes in total); other ranks get None.  `counts` = slab sizes of all ranks."""
     if not (dist.is_available() and dist.is_initialized()):
         return sdf_slab
     world = dist.get_world_size()
+    if dst is not None:
+        parts = _p2p_gather(sdf_slab, counts, dst)
+        return torch.cat(parts) if dist.get_rank() == dst else None
     m = max(counts)
     pad = torch.zeros(m, dtype=sdf_slab.dtype, device=sdf_slab.device)
     pad[:sdf_slab.numel()] = sdf_slab
@@ -47,15 +91,14 @@ def gather_band(sdf_slab, counts, device=None):
 def gather_meshes(meshes, dst=0):
     """The "final mesh gather" of the shape-sharded run: every rank holds the meshes of its own
     shapes as a list of (shape_index, verts [V,3] fp32, faces [F,3] int32) tensors on its device; rank `dst` receives
-    all of them, ordered by shape index, other ranks receive [].  One all_gather of the per-rank size table, then one
-    padded all_gather per buffer kind (NCCL over NVLink on GPUs, gloo on CPU) -- meshes are O(res^2) small, so a single
-    padded exchange beats per-mesh point-to-point sends."""
+    all of them, ordered by shape index, other ranks receive [].  One small all_gather of the size table (so that dst can
+    size its receive buffers), then each rank sends its concatenated vertex and face buffers to dst point-to-point: the
+    bytes on the wire are the mesh bytes, once (a padded all_gather would replicate every mesh to every rank)."""
     if not (dist.is_available() and dist.is_initialized()):
         return sorted(meshes, key=lambda m: m[0])
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = meshes[0][1].device if meshes else (torch.device('cuda', torch.cuda.current_device())
                                               if dist.get_backend() == 'nccl' else torch.device('cpu'))
-    # size table: [n_meshes, then (shape_index, V, F) per mesh], padded to the largest mesh count
     n_local = torch.tensor([len(meshes)], dtype=torch.int64, device=dev)
     n_all = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(n_all, n_local)
@@ -65,27 +108,26 @@ def gather_meshes(meshes, dst=0):
         table[i] = torch.tensor([idx, v.shape[0], f.shape[0]], dtype=torch.int64)
     tables = [torch.zeros_like(table) for _ in range(world)]
     dist.all_gather(tables, table)
-    tot_v = [int(t[:int(n.item()), 1].sum()) for t, n in zip(tables, n_all)]
-    tot_f = [int(t[:int(n.item()), 2].sum()) for t, n in zip(tables, n_all)]
-    vbuf = torch.zeros((max(max(tot_v), 1), 3), dtype=torch.float32, device=dev)
-    fbuf = torch.zeros((max(max(tot_f), 1), 3), dtype=torch.int32, device=dev)
+    tables = [t.cpu() for t in tables]
+    n_all = [int(n.item()) for n in n_all]
+    tot_v = [int(t[:n, 1].sum()) for t, n in zip(tables, n_all)]
+    tot_f = [int(t[:n, 2].sum()) for t, n in zip(tables, n_all)]
     if meshes:
         vcat = torch.cat([m[1].reshape(-1, 3).to(torch.float32) for m in meshes])
         fcat = torch.cat([m[2].reshape(-1, 3).to(torch.int32) for m in meshes])
-        vbuf[:vcat.shape[0]] = vcat
-        fbuf[:fcat.shape[0]] = fcat
-    vall = [torch.empty_like(vbuf) for _ in range(world)]
-    fall = [torch.empty_like(fbuf) for _ in range(world)]
-    dist.all_gather(vall, vbuf)
-    dist.all_gather(fall, fbuf)
+    else:
+        vcat = torch.zeros((0, 3), dtype=torch.float32, device=dev)
+        fcat = torch.zeros((0, 3), dtype=torch.int32, device=dev)
+    vall = _p2p_gather(vcat, tot_v, dst)
+    fall = _p2p_gather(fcat, tot_f, dst)
     if rank != dst:
         return []
     out = []
     for r in range(world):
         vo = fo = 0
-        for i in range(int(n_all[r].item())):
+        for i in range(n_all[r]):
             idx, nv, nf = (int(x) for x in tables[r][i])
-            out.append((idx, vall[r][vo:vo + nv].clone(), fall[r][fo:fo + nf].clone()))
+            out.append((idx, vall[r][vo:vo + nv], fall[r][fo:fo + nf]))
             vo += nv
             fo += nf
     return sorted(out, key=lambda m: m[0])

@@ -175,6 +175,50 @@ def gen_ball():
     print('ball.npz written: oracle == reference')
 
 
+def gen_rotation():
+    """The non-reconstruction pass of the reference dataset (reconstruction=False: per-sample random rotation of patch,
+    sub-sample and query, source/data_loader.py:381-393) on the 6 000-point abc subset: rotated patches and query points of
+    the first queries.  (trimesh is absent: random_rotation_matrix / transform_points are the shim's restatement of
+    trimesh.transformations; what this pins is the reference's stream consumption, application order and conventions.)"""
+    cloud = np.load(os.path.join(HERE, 'assembly.npz'))['cloud']
+    seed, k, S, n = 40938661, 300, 1000, 8
+    rng = np.random.RandomState(3)
+    qpts = (cloud[rng.choice(len(cloud), 40, replace=False)] + rng.normal(0, 0.02, (40, 3))).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        for sub in ('04_pts', '05_query_pts', '05_query_dist'):
+            os.makedirs(os.path.join(d, sub))
+        np.save(os.path.join(d, '04_pts', 'shape.xyz.npy'), cloud)
+        np.save(os.path.join(d, '05_query_pts', 'shape.ply.npy'), qpts)
+        np.save(os.path.join(d, '05_query_dist', 'shape.ply.npy'), rng.normal(0, 0.01, 40).astype(np.float32))
+        with open(os.path.join(d, 'testset.txt'), 'w') as f:
+            f.write('shape\n')
+        ds = ref_dl.PointcloudPatchDataset(
+            root=d, shape_list_filename='testset.txt', points_per_patch=k, patch_radius=0.0,
+            patch_features=['imp_surf_magnitude', 'imp_surf_sign', 'patch_pts_ids', 'p_index'],
+            epsilon=3, seed=seed, center='mean', cache_capacity=5, pre_processed_patches=True,
+            query_grid_resolution=None, sub_sample_size=S, reconstruction=False,
+            uniform_subsample=1, fixed_subsample=0, num_workers=0)
+        items = [ds[i] for i in range(n)]
+    from points2surf_b200 import eval as my_eval
+    R = my_eval._random_rotations(np.random.RandomState(seed), n)
+    kd = orc.make_kdtree(cloud)
+    for i, it in enumerate(items):
+        _, patch_ps, radius = orc.knn_patch(cloud, kd, qpts[i], k)
+        want = (R[i].astype(np.float64) @ patch_ps.astype(np.float64).T).T
+        assert np.abs(it['patch_pts_ps'].numpy() - want).max() < 1e-6, i
+        assert np.abs(it['imp_surf_query_point_ms'].numpy() - R[i].astype(np.float64) @ qpts[i].astype(np.float64)).max() < 1e-6
+        # the rotated sub-sample is a rotation of cloud rows: un-rotate and look the rows up
+        back = (R[i].astype(np.float64).T @ it['pts_sub_sample_ms'].numpy().astype(np.float64).T).T
+        dist, _ = kd.query(back, 1)
+        assert dist.max() < 1e-5
+    np.savez_compressed(os.path.join(HERE, 'rotation.npz'), seed=seed, k=k, query_pts=qpts[:n],
+                        patch_rot=np.stack([it['patch_pts_ps'].numpy() for it in items]),
+                        query_rot=np.stack([it['imp_surf_query_point_ms'].numpy() for it in items]),
+                        radius=np.array([np.float32(it['patch_radius_ms'].numpy()) for it in items]),
+                        dist_sign=np.array([float(it['imp_surf_dist_sign_ms'].numpy()[0]) for it in items]))
+    print('rotation.npz written: mirror rotations == reference dataset (reconstruction=False)')
+
+
 def gen_volume():
     out = {}
     for name, res, noise in (('sphere', 32, 0.0), ('noisy', 40, 0.15)):

@@ -117,3 +117,26 @@ def test_unsupported_options_raise(tmp_path):
     opt.reconstruction = True
     with pytest.raises(ValueError):
         p2s_eval.points_to_surf_eval(opt)
+
+
+def test_rotation_augmented_pass_matches_reference_dataset():
+    """full_eval's non-reconstruction pass (full_eval.py:31-41): the reference dataset rotates patch, sub-sample and query by
+    a per-sample random rotation (data_loader.py:381-393).  The mirror's rotations (stream, order, conventions) applied
+    to the GPU kNN patches reproduce tests/golden/rotation.npz, made by the unmodified dataset class; float32 rotation
+    here vs float64-then-cast there: tolerance 1e-6."""
+    g = load_golden('rotation.npz')
+    cloud = load_golden('assembly.npz')['cloud']
+    q = torch.from_numpy(g['query_pts']).cuda()
+    pts = torch.from_numpy(cloud).cuda()
+    from points2surf_b200 import ops
+    _, patch, radius = ops.knn_patch(pts, q, int(g['k']))
+    assert np.array_equal(radius.cpu().numpy(), g['radius'])
+    R = torch.from_numpy(p2s_eval._random_rotations(np.random.RandomState(int(g['seed'])), q.shape[0])).cuda()
+    sub = ops.gather_points(pts, ops.subsample(pts, q, 1000, True, 1))
+    patch_r, sub_r, q_r = p2s_eval._rotate_inputs(patch, sub, q, R)
+    assert np.abs(patch_r.cpu().numpy() - g['patch_rot']).max() < 1e-6
+    assert np.abs(q_r.cpu().numpy() - g['query_rot']).max() < 1e-6
+    # rotations preserve the geometry the network sees: distances to the (rotated) query are unchanged
+    d0 = (sub - q[:, None, :]).norm(dim=2)
+    d1 = (sub_r - q_r[:, None, :]).norm(dim=2)
+    assert torch.allclose(d0, d1, atol=1e-5)

@@ -29,7 +29,7 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 SEED = 40938661          # bench.py --seed default
 FP32_AMBIGUOUS = 2e-3    # |sign logit| below which two fp32 implementations may disagree on the sign
-MAX_VOXELS = {128: 0.25, 256: 0.5}   # max |d SDF| of the tc engine vs the fp32 oracle, in voxels (measured: see DESIGN.md section 2)
+MAX_VOXELS = {128: 0.4, 256: 0.6}   # max |d SDF| of the tc engine vs the fp32 oracle, in voxels (measured: see DESIGN.md section 2)
 
 
 def cu(a):

@@ -246,10 +246,14 @@ def test_reconstruct_matches_stagewise_oracle(variant):
 
 # ------------------------------------------------------------------ a12 : marching cubes (oracle unpinned vs skimage)
 # vertices: fp32 interpolation on both sides, tolerance 1e-6 absolute in model space; faces: identical indices.
-@pytest.mark.parametrize('case', ['sphere', 'noise', 'propagated'])
+@pytest.mark.parametrize('case', ['sphere', 'noise', 'propagated', 'all_cases'])
 def test_marching_cubes_matches_oracle(case):
     from oracle import mc_oracle as mc
-    if case == 'sphere':
+    from oracle import mc_topo
+    if case == 'all_cases':
+        # every corner-sign configuration with random magnitudes (ambiguous faces on both sides of the decider), exact zeros
+        vol = mc_topo.all_cases_volume(0)
+    elif case == 'sphere':
         R = 40
         g = (np.arange(R) + 0.5) / R * 2 - 1
         X, Y, Z = np.meshgrid(g, g, g, indexing='ij')
@@ -268,6 +272,18 @@ def test_marching_cubes_matches_oracle(case):
     assert np.array_equal(f.cpu().numpy(), fo)
     np.testing.assert_allclose(v.cpu().numpy(), vo, rtol=0, atol=1e-6)
     assert mc.mesh_is_closed(f.cpu().numpy())
+    # the table-free second restatement (oracle/mc_topo.py: polygons traced on the cell values, asymptotic decider on
+    # ambiguous faces) shares nothing with tools/gen_mc_tables.py: same vertices, same triangles
+    vt, ft, st = mc_topo.marching_cubes(vol, 0.0, 'asymptotic', return_stats=True)
+    assert np.array_equal(v.cpu().numpy(), vt) or np.abs(v.cpu().numpy() - vt).max() <= 1e-6
+    assert np.array_equal(mc_topo.triangle_set(f.cpu().numpy()), mc_topo.triangle_set(ft))
+    # and where the classic rule (always separate the positive corners) would have given another mesh
+    vc, fc = mc_topo.marching_cubes(vol, 0.0, 'separate_positive')
+    same = np.array_equal(mc_topo.triangle_set(fc), mc_topo.triangle_set(ft))
+    print('%s: %d cells, %d with ambiguous faces, %d with more than one sheet; Euler characteristic asymptotic %d / classic %d; '
+          'classic rule gives %s mesh' % (case, st['cells'], st['ambiguous_face_cells'], st['multi_sheet_cells'],
+                                          mc_topo.euler_characteristic(len(vt), ft), mc_topo.euler_characteristic(len(vc), fc),
+                                          'the same' if same else 'a different'))
 
 
 def test_marching_cubes_empty_volume():

@@ -135,3 +135,23 @@ def test_ball_patch_oracle_matches_reference_golden():
             ids, patch, cnt = orc.ball_patch(cloud, kd, qall[qi], radius, P, rng)
             assert cnt == int(g[tag + '_counts'][j])
             assert np.array_equal(patch, g[tag + '_patch_ps'][j])
+
+
+def test_marching_cubes_table_oracle_matches_table_free_restatement():
+    """oracle/mc_oracle.py (table from tools/gen_mc_tables.py, shared with the CUDA kernel) against oracle/mc_topo.py (no
+    table: polygons traced on the cell values) on every corner-sign configuration with random magnitudes, and on noise."""
+    from oracle import mc_oracle as mc, mc_topo
+    rng = np.random.RandomState(0)
+    noise = rng.standard_normal((17, 17, 17)).astype(np.float32)
+    noise[[0, -1]] = -1; noise[:, [0, -1]] = -1; noise[:, :, [0, -1]] = -1
+    for vol in (mc_topo.all_cases_volume(0), mc_topo.all_cases_volume(3), noise):
+        v0, f0 = mc.marching_cubes(vol, 0.0)
+        v1, f1, st = mc_topo.marching_cubes(vol, 0.0, 'asymptotic', return_stats=True)
+        assert np.array_equal(v0, v1) and np.array_equal(f0, f1)
+        assert mc.mesh_is_closed(f0) and st['ambiguous_face_cells'] > 100
+        # the classic reading of ambiguous faces is a different surface on these volumes (documented in DESIGN.md)
+        _, f2 = mc_topo.marching_cubes(vol, 0.0, 'separate_positive')
+        assert mc.mesh_is_closed(f2) and not np.array_equal(mc_topo.triangle_set(f1), mc_topo.triangle_set(f2))
+    # exact zeros are not positive: an isolated zero voxel in a negative region produces no surface
+    z = np.full((6, 6, 6), -1.0, np.float32); z[3, 3, 3] = 0.0
+    assert mc_topo.marching_cubes(z, 0.0)[1].shape[0] == 0 and mc.marching_cubes(z, 0.0)[1].shape[0] == 0

@@ -29,6 +29,12 @@ def _worker(rank, world, port, q):
         slab = full[first:first + count].clone()                      # stand-in for Engine.reconstruct(first, count)
         counts = [sharding.query_slab(Q, r, world)[1] for r in range(world)]
         band = sharding.gather_band(slab, counts)
+        band_dst = sharding.gather_band(slab, counts, dst=1)          # only the meshing rank receives
+        assert (band_dst is None) if rank != 1 else bool(torch.equal(band_dst, full))
+        # LPT: deterministic, identical on every rank, balanced
+        bins, tot = sharding.lpt_assign([90, 10, 40, 60, 50, 50], world)
+        assert sorted(sum(bins, [])) == list(range(6)) and abs(tot[0] - tot[1]) <= 10
+        assert sharding.shapes_for_rank(6, rank, world, loads=[90, 10, 40, 60, 50, 50]) == bins[rank]
         ms, units = sharding.reduce_timing(10.0 + rank, count)
         # final mesh gather: rank r owns shapes r, r+2, ... of 5; mesh i has i+1 vertices and 2i faces (shape 0: no faces)
         mine = [(i, torch.full((i + 1, 3), float(i)), torch.full((2 * i, 3), i, dtype=torch.int32))

@@ -4,14 +4,17 @@ Cube corner c = x + 2y + 4z.  Edge e = 4*axis + (the two other coordinates of it
 axis 0: e = 0 + (y + 2z); axis 1: e = 4 + (x + 2z); axis 2: e = 8 + (x + 2y).
 Case index = bitmask of corners whose value is > level ("positive").
 
-Construction (Lorensen & Cline 1987 cases with a face-consistent ambiguity rule, cf. Montani et al. 1994):
-on every cube face, viewed from outside with the corners in counter-clockwise order, each maximal run of
-positive corners contributes one oriented iso-segment from the edge where the run is left to the edge where
-it is entered (positive on the left).  Ambiguous faces (+-+-) therefore always separate the positive corners;
-the rule depends on the face's corner signs only, so neighbouring cells agree and the surface is watertight.
-Segments chain into closed loops, each loop is fan-triangulated.  All cells use the same orientation rule, so
-the mesh is consistently oriented; the global sign is fixed afterwards by the signed volume
-(trimesh.repair.fix_inversion in the reference, source/sdf.py:226).
+Construction: on every cube face each maximal run of positive corners contributes one oriented iso-segment from the
+edge where the run is left to the edge where it is entered.  An AMBIGUOUS face (+-+-) has two readings: the positive
+corners are separated (the rule above, Lorensen & Cline 1987 / Montani et al. 1994) or joined through the face, in
+which case each NEGATIVE corner is cut off instead.  Which reading applies is decided at run time from the face's four
+VALUES by the asymptotic decider (sign of the bilinear interpolant at its saddle: Nielson & Hamann 1991; the face test
+of Lewiner et al. 2003, i.e. of the skimage call the reference makes, source/sdf.py:215).  The decision depends on
+the shared face only, so neighbouring cells agree and the surface is watertight.  The table therefore has one row per
+(case, decision bits of the case's ambiguous faces in ascending face order).  Segments chain into closed loops, each
+loop is fan-triangulated from its smallest edge label.  All cells use the same orientation rule, so the mesh is
+consistently oriented; the global sign is fixed afterwards by the signed volume (trimesh.repair.fix_inversion in the
+reference, source/sdf.py:226).  The interior test of MC33 (tunnels inside a cell) is not part of the table.
 
 Writes points2surf_b200/csrc/mc_tables.cuh and oracle/mc_tables.py.
 """
@@ -71,12 +74,23 @@ def faces():
 FACES = faces()
 
 
-def case_triangles(mask):
+def ambiguous_faces(mask):
+    pos = [(mask >> c) & 1 for c in range(8)]
+    return [f for f, ring in enumerate(FACES) if sum(pos[c] for c in ring) == 2 and pos[ring[0]] == pos[ring[2]]]
+
+
+def case_triangles(mask, joined=()):
+    """`joined`: indices of ambiguous faces whose positive corners are joined through the face."""
     pos = [(mask >> c) & 1 for c in range(8)]
     nxt = {}
-    for ring in FACES:
+    for f, ring in enumerate(FACES):
         sg = [pos[c] for c in ring]
         if sum(sg) in (0, 4):
+            continue
+        if f in joined:
+            for k in range(4):      # cut off each negative corner
+                if not sg[k]:
+                    nxt[edge_between(ring[(k - 1) % 4], ring[k])] = edge_between(ring[k], ring[(k + 1) % 4])
             continue
         for i in range(4):
             # start of a maximal positive run: corner i positive, previous corner negative
@@ -106,32 +120,49 @@ def case_triangles(mask):
 
 
 def main():
-    table = [case_triangles(m) for m in range(256)]
-    assert max(len(t) for t in table) <= 5
-    counts = [len(t) for t in table]
+    rows, base, amb_mask = [], [], []
+    for m in range(256):
+        amb = ambiguous_faces(m)
+        base.append(len(rows))
+        amb_mask.append(sum(1 << f for f in amb))
+        for bits in range(1 << len(amb)):
+            joined = tuple(f for k, f in enumerate(amb) if (bits >> k) & 1)
+            rows.append(case_triangles(m, joined))
+    max_t = max(len(t) for t in rows)
+    assert max_t <= 12 and len(rows) < 65536
+    counts = [len(t) for t in rows]
+    width = 3 * max_t
     flat = []
-    for t in table:
+    for t in rows:
         row = [i for tri in t for i in tri]
-        row += [-1] * (16 - len(row))
-        flat.append(row)
+        flat.append(row + [-1] * (width - len(row)))
     hdr = ['// GENERATED by tools/gen_mc_tables.py -- do not edit.',
            '// corner c = x + 2y + 4z; edge e = 4*axis + low bits of the other two coordinates of its lower end;',
-           '// case = bitmask of corners with value > level; rows hold up to 5 triangles of edge ids, -1 terminated.',
+           '// case = bitmask of corners with value > level.  Row of (case, decisions) = kMcRowBase[case] + sum over the set bits of',
+           '// kMcAmbMask[case] (ascending face index k-th set bit) of (positive corners of that face joined ? 1 << k : 0);',
+           '// a row holds kMcTriCount[row] triangles of edge labels.  kMcFaceRing[f] = the four corners of face f in cyclic order.',
            '#pragma once', '#include <cstdint>', 'namespace p2s {',
-           '__device__ __constant__ int8_t kMcTriTable[256][16] = {']
+           'constexpr int kMcRows = %d, kMcMaxTris = %d;' % (len(rows), max_t),
+           '__device__ __constant__ uint16_t kMcRowBase[256] = {', '    ' + ', '.join(str(b) for b in base), '};',
+           '__device__ __constant__ uint8_t kMcAmbMask[256] = {', '    ' + ', '.join(str(b) for b in amb_mask), '};',
+           '__device__ __constant__ uint8_t kMcFaceRing[6][4] = {', '    ' + ', '.join('{%d, %d, %d, %d}' % tuple(r) for r in FACES), '};',
+           '__device__ __constant__ int8_t kMcTriTable[kMcRows][%d] = {' % width]
     for row in flat:
         hdr.append('    {' + ', '.join('%2d' % v for v in row) + '},')
-    hdr += ['};', '__device__ __constant__ uint8_t kMcTriCount[256] = {',
+    hdr += ['};', '__device__ __constant__ uint8_t kMcTriCount[kMcRows] = {',
             '    ' + ', '.join(str(c) for c in counts), '};', '}  // namespace p2s', '']
     with open(os.path.join(ROOT, 'points2surf_b200', 'csrc', 'mc_tables.cuh'), 'w') as f:
         f.write('\n'.join(hdr))
     with open(os.path.join(ROOT, 'oracle', 'mc_tables.py'), 'w') as f:
         f.write('"""GENERATED by tools/gen_mc_tables.py -- do not edit.  TEST INFRASTRUCTURE (oracle side)."""\n')
-        f.write('import numpy as np\n\nTRI_TABLE = np.array([\n')
+        f.write('import numpy as np\n\nROW_BASE = np.array([' + ', '.join(str(b) for b in base) + '], dtype=np.int32)\n')
+        f.write('AMB_MASK = np.array([' + ', '.join(str(b) for b in amb_mask) + '], dtype=np.int32)\n')
+        f.write('FACE_RING = np.array(' + repr([list(r) for r in FACES]) + ', dtype=np.int32)\n')
+        f.write('TRI_TABLE = np.array([\n')
         for row in flat:
             f.write('    [' + ', '.join('%2d' % v for v in row) + '],\n')
         f.write('], dtype=np.int8)\nTRI_COUNT = np.array([' + ', '.join(str(c) for c in counts) + '], dtype=np.int32)\n')
-    print('cases with triangles:', sum(1 for c in counts if c), 'max tris', max(counts), 'total', sum(counts))
+    print('rows', len(rows), 'max tris', max_t, 'total tris', sum(counts), 'table bytes', len(rows) * width)
 
 
 if __name__ == '__main__':
