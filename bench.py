@@ -49,6 +49,7 @@ def parse():
     ap.add_argument('--mix_shapes', action='store_true', help='sphere / torus / box per rank instead of same-size spheres')
     ap.add_argument('--cpu_sample', type=int, default=256, help='queries in the bounded CPU-baseline sample')
     ap.add_argument('--seed', type=int, default=40938661)
+    ap.add_argument('--batch', type=int, default=0, help='queries per network batch (0 = library default 8192)')
     ap.add_argument('--workload', default='headline', choices=['headline', 'sharded'],
                     help="'sharded': only the shape-sharded job (configs 3 / 5: --model, --shapes_per_gpu, --grid_res), shapes/s")
     ap.add_argument('--shapes_per_gpu', type=int, default=2)
@@ -363,11 +364,11 @@ def run_b200(args):
     host_sdf = torch.empty(Q, dtype=torch.float32).pin_memory()
 
     def step_dev():
-        return eng.reconstruct(pts, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q)
+        return eng.reconstruct(pts, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q, batch=args.batch)
 
     def step_host():
         return eng.reconstruct_host(host_cloud.numpy(), args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, cap=Q,
-                                    out_lin=host_lin.numpy(), out_sdf=host_sdf.numpy())
+                                    out_lin=host_lin.numpy(), out_sdf=host_sdf.numpy(), batch=args.batch)
 
     def barrier():
         if world > 1:

@@ -39,6 +39,7 @@ struct Ctrl {
     unsigned nonzero_seen;      // some sample is not exactly 0 (sdf.py:187-189)
     unsigned bad_index;         // scatter: number of voxel indices outside [0, res^3)
     unsigned long long visits;  // tile evaluations (diagnostics)
+    unsigned long long t_total, t_sync, t_first;   // diagnostics (ns, block 0): kernel, time inside grid.sync(), first iteration
 };
 
 __global__ void any_nonzero_kernel(const float* __restrict__ sdf, int64_t Q, Ctrl* c) {
@@ -126,6 +127,10 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
     long long totalN = 0;                                               // zero count of the vote (whole volume)
     long long totalS = (long long)__ldcg(&p.ctrl->cntS0);               // zero count of the signs
     int iters = 0, final_buf = 0, error = 0;
+    auto now_ns = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    const bool diag = blockIdx.x == 0 && tid == 0;
+    const unsigned long long t_begin = diag ? now_ns() : 0ull;
+    unsigned long long t_sync = 0;
     for (int it = 0;; ++it) {
         const int cur = it % 3, nxt = (it + 1) % 3;
         if (totalS == 0) { final_buf = it & 1; break; }                 // `if unknown_before.sum() == 0: break`
@@ -267,14 +272,16 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
             }
             __syncthreads();
         }
+        const unsigned long long ts = diag ? now_ns() : 0ull;
         grid.sync();
+        if (diag) { t_sync += now_ns() - ts; if (it == 0) p.ctrl->t_first = now_ns() - t_begin; }
         totalN += __ldcg(&p.ctrl->dN[cur]);
         const long long afterS = totalS + __ldcg(&p.ctrl->dS[cur]);
         if (totalN >= totalS) { final_buf = it & 1; break; }            // `if unknown_after.sum() >= unknown_before.sum(): break`
         totalS = afterS;
         ++iters;
     }
-    if (blockIdx.x == 0 && tid == 0) { p.ctrl->iters = iters; p.ctrl->final_buf = final_buf; p.ctrl->error = error; }
+    if (blockIdx.x == 0 && tid == 0) { p.ctrl->iters = iters; p.ctrl->final_buf = final_buf; p.ctrl->error = error; p.ctrl->t_total = now_ns() - t_begin; p.ctrl->t_sync = t_sync; }
 }
 
 // the reference raises IndexError for an index >= res and wraps a negative one (sdf.py:95-111); here both are counted and
@@ -373,8 +380,9 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     {
         static int stats = -1;
         if (stats < 0) { const char* e = getenv("P2S_VOL_STATS"); stats = (e && e[0] == '1') ? 1 : 0; }
-        if (stats) fprintf(stderr, "p2s sign propagation: res %d, %d iterations, %llu tile evaluations over %d tiles (%.1f per tile; a full sweep per iteration would be %d), grid %u x %d threads, %zu B smem\n",
-                           res, h.iters, h.visits, numTiles, (double)h.visits / numTiles, h.iters + 1, grid, kPropThreads, smem);
+        if (stats) fprintf(stderr, "p2s sign propagation: res %d, %d iterations, %llu tile evaluations over %d tiles (%.1f per tile; a full sweep per iteration would be %d), grid %u x %d threads, %zu B smem; kernel %.3f ms (block 0: %.3f ms inside grid.sync, first iteration %.3f ms)\n",
+                           res, h.iters, h.visits, numTiles, (double)h.visits / numTiles, h.iters + 1, grid, kPropThreads, smem,
+                           h.t_total * 1e-6, h.t_sync * 1e-6, h.t_first * 1e-6);
     }
     if (Q > 0 && !h.nonzero_seen) {
         // the reference prints a warning and returns without writing anything (sdf.py:187-189)
