@@ -254,7 +254,7 @@ void p2s_model_destroy(p2s_model* mm) {
     tc_destroy(*m);
     if (m->blob) cudaFree(m->blob);
     if (m->guard_count_dev) cudaFree(m->guard_count_dev);
-    m->ws_net.release(); m->ws_io.release(); m->ws_misc.release(); m->ws_guard.release(); m->ws_stash.release(); m->ws_host.release();
+    m->ws_net.release(); m->ws_io.release(); m->ws_misc.release(); m->ws_guard.release(); m->ws_host.release();
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
 }

@@ -41,7 +41,6 @@ struct Model {
     DevBuf ws_io;                        // staged host inputs / assembled query batches
     DevBuf ws_misc;
     DevBuf ws_guard;
-    DevBuf ws_stash;                     // conv0b activations handed from the STN pass to the final pass (fp16)
     DevBuf ws_host;                      // device staging of host-call inputs/outputs
     int64_t* guard_count_dev = nullptr;
     int64_t last_guard_count = 0;

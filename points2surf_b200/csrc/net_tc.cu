@@ -24,7 +24,6 @@
 // The small per-query FC tails between the passes run as fp32 FMA GEMMs (net_fp32.cu kernels).
 #include "model.cuh"
 #include "tc_ptx.cuh"
-#include <algorithm>
 
 #ifndef P2S_TC_BOUNDED_WAIT
 #define P2S_TC_BOUNDED_WAIT 1   // trap instead of hanging if a barrier protocol bug slips in
@@ -89,9 +88,6 @@ struct PassParams {
     const uint8_t* w3_img;     // [8 chunks][32768 B] (precise: [8][hi | lo])  (K-major, LBO 128, SBO 2048)
     float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer)
     long long* wstats;         // diagnostics: per-role barrier wait cycles (null = off)
-    uint8_t* stash_out;        // STN pass: fp16 output of the first mid layer (conv0b), [query][tile][point][64 ch] = 128 B rows (null = off)
-    const uint8_t* stash_in;   // final pass: that stash replaces the first layer and conv0b (the stack then starts at conv1*T)
-    int opt;                   // experiment switches (env P2S_TC_OPT, default all on): bit 0 = 64-column epilogue rounds, bit 1 = conv0b stash between the STN and the final pass
 };
 
 struct Bars {
@@ -339,11 +335,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
         for (int it = c; it < ntiles; it += 2) {
             const uint32_t ab = PRECISE ? 0u : (uint32_t)c;                              // activation buffer of this tile
             const uint32_t au = PRECISE ? (uint32_t)it : ((uint32_t)it >> 1);           // its use count
-            uint8_t* stash_row = nullptr;                                               // this point's 128 B row of the conv0b stash
-            if (!PRECISE && p.stash_out && part == 0) {
-                const int qi = it / tpq, tq = it - qi * tpq;
-                stash_row = p.stash_out + ((((size_t)stream + (size_t)qi * nstreams) * tpq + tq) * kTile + pt) * 128;
-            }
             // ---- mid layers
             int boff = 0;
             for (int l = 0; l < p.num_mid; ++l, ++round) {
@@ -357,8 +348,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
                 const bool small = !PRECISE && (N == 64);
                 const uint32_t dcol = small ? kColDmidB : kColDmid;
-                // 32 accumulator columns -> bias, ReLU, fp16 pack -> next operand (TMEM) or the big layer's B operand (smem)
-                auto process32 = [&](const int n0, const uint32_t (&r)[32]) {
+                for (int n0 = 0; n0 < N; n0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem + lane_base + dcol + n0, r);
+                    tmem_ld_wait();
+                    if (n0 + 32 >= N) {            // accumulator fully read: hand it to the other chain
+                        tc_fence_before();
+                        mbar_arrive(&bars->dmid_free[small ? 1 : 0]);
+                    }
                     uint32_t v[16], vl[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -372,11 +369,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                             v[2 * j4] = pack_relu(s01.x, s01.y);
                             v[2 * j4 + 1] = pack_relu(s23.x, s23.y);
                         }
-                    }
-                    if (!PRECISE && l == 0 && stash_row) {     // conv0b output, channel pairs n0/2 .. n0/2+15 of this point
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(stash_row + n0 * 2 + j * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                     if (!last) {
                         // next layer's A operand (K index = channel, columns hold channel pairs); the MMA that read
@@ -402,33 +394,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                             if (PRECISE)   // lo image of the single activation buffer
                                 *reinterpret_cast<uint4*>(dst + kAct2Bytes + (uint32_t)(n0 / 8 + j) * 128u) = make_uint4(vl[4 * j], vl[4 * j + 1], vl[4 * j + 2], vl[4 * j + 3]);
                         }
-                    }
-                };
-                if (PRECISE || !(p.opt & 1)) {
-                    for (int n0 = 0; n0 < N; n0 += 32) {
-                        uint32_t r[32];
-                        tmem_ld_x32(tmem + lane_base + dcol + n0, r);
-                        tmem_ld_wait();
-                        if (n0 + 32 >= N) {            // accumulator fully read: hand it to the other chain
-                            tc_fence_before();
-                            mbar_arrive(&bars->dmid_free[small ? 1 : 0]);
-                        }
-                        process32(n0, r);
-                    }
-                } else {
-                    // N is 64 or 128: two 32-column loads in flight per round (the chain is latency-bound: one TMEM round
-                    // trip per 64 columns instead of one per 32)
-                    for (int n0 = 0; n0 < N; n0 += 64) {
-                        uint32_t r0[32], r1[32];
-                        tmem_ld_x32(tmem + lane_base + dcol + n0, r0);
-                        tmem_ld_x32(tmem + lane_base + dcol + n0 + 32, r1);
-                        tmem_ld_wait();
-                        if (n0 + 64 >= N) {
-                            tc_fence_before();
-                            mbar_arrive(&bars->dmid_free[small ? 1 : 0]);
-                        }
-                        process32(n0, r0);
-                        process32(n0 + 32, r1);
                     }
                 }
                 if (!last) {
@@ -468,27 +433,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             cx = cy = cz = 0.f;
             if (sg.center) { cx = p.query[q2 * 3 + 0]; cy = p.query[q2 * 3 + 1]; cz = p.query[q2 * 3 + 2]; }
         };
-        if (!PRECISE && p.stash_in) {
-            // final pass fed from the STN pass's conv0b stash: the operand of the first mid layer is a 128 B row per point
-            for (int it = 0; it < ntiles; ++it) {
-                const int c = it & 1;
-                const int qi = it / tpq, tq = it - qi * tpq;
-                const uint4* row = reinterpret_cast<const uint4*>(p.stash_in + ((((size_t)stream + (size_t)qi * nstreams) * tpq + tq) * kTile + pt) * 128);
-                uint32_t v[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 u = __ldg(row + j);
-                    v[4 * j] = u.x; v[4 * j + 1] = u.y; v[4 * j + 2] = u.z; v[4 * j + 3] = u.w;
-                }
-                wait_bar(&bars->a_free[c], (((uint32_t)it >> 1) & 1) ^ 1, wsp ? wsp + WS_A_FREE : nullptr);
-                tc_fence_after();
-                tmem_st_x32(tmem + lane_base + kColA + (uint32_t)c * C::kACols, v);
-                tmem_st_wait();
-                if (p.num_mid == 1) wait_bar(&bars->act2_empty[c], (((uint32_t)it >> 1) & 1) ^ 1, wsp ? wsp + WS_ACT2_EMPTY : nullptr);
-                tc_fence_before();
-                mbar_arrive(&bars->a_ready[c]);
-            }
-        } else {
         float x = 0.f, y = 0.f, z = 0.f, pcx = 0.f, pcy = 0.f, pcz = 0.f;
         if (ntiles > 0) fetch(0, x, y, z, pcx, pcy, pcz);
         for (int it = 0; it < ntiles; ++it) {
@@ -546,7 +490,6 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
             if (p.num_mid == 1) wait_bar(&bars->act2_empty[PRECISE ? 0 : c], ((PRECISE ? (uint32_t)it : ((uint32_t)it >> 1)) & 1) ^ 1, wsp ? wsp + WS_ACT2_EMPTY : nullptr);
             tc_fence_before();
             mbar_arrive(&bars->a_ready[c]);
-        }
         }
     } else {
         // =============================================================== big-layer epilogue: max over the tile's points
@@ -782,28 +725,20 @@ uint8_t* pack_w3(TcWeights& t, const Layer& L, bool split = false) {   // 8 chun
 }
 
 void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const float* query, const float* R,
-                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st, bool precise,
-                 uint8_t* stash_out = nullptr, const uint8_t* stash_in = nullptr) {
+                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st, bool precise) {
     PassParams p{};
     p.seg[0] = s0; p.seg[1] = s1;
     p.query = query; p.R = R;
     p.tiles_per_query = s0.tiles + s1.tiles;
     p.B = (int)B;
     p.W0 = s.W0; p.b0 = s.b0;
-    p.stash_out = stash_out; p.stash_in = stash_in;
-    // fed from the stash, the stack starts behind its first mid layer (conv0b)
-    const int skip = stash_in ? 1 : 0;
-    p.num_mid = s.num_mid - skip;
-    for (int l = 0; l + skip < 3; ++l) {
-        p.mid_N[l] = s.mid_N[l + skip]; p.mid_img[l] = precise ? s.mid_img_p[l + skip] : s.mid_img[l + skip]; p.mid_bias[l] = s.mid_bias[l + skip];
-    }
-    perq_layer -= (perq_layer >= 0 ? skip : 0);
+    p.num_mid = s.num_mid;
+    for (int l = 0; l < 3; ++l) { p.mid_N[l] = s.mid_N[l]; p.mid_img[l] = precise ? s.mid_img_p[l] : s.mid_img[l]; p.mid_bias[l] = s.mid_bias[l]; }
     p.perq_layer = perq_layer;
     p.perq_img = perq_img;
     p.w3_img = precise ? s.w3_img_p : s.w3_img;
     p.out = out;
     p.wstats = nullptr;
-    { const char* e = getenv("P2S_TC_OPT"); p.opt = e ? atoi(e) : 0x7fffffff; }   // read per launch: tests toggle it
     TcWeights& t = *m.tc;
     static int wstats_on = -1;
     if (wstats_on < 0) { const char* e = getenv("P2S_TC_WAITSTATS"); wstats_on = (e && e[0] == '1') ? 1 : 0; }
@@ -836,7 +771,7 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
         P2S_CUDA(cudaStreamSynchronize(st));
         static const char* roles[6] = {"big-issuer", "mid-issuer", "chain0", "chain1", "first-layer", "colmax"};
         static const char* slots[WS_TOTAL] = {"act2_full", "d3_empty", "dmid_free", "dmid_ready", "act2_empty", "a_free", "d3_full"};
-        fprintf(stderr, "p2s waitstats: pass num_mid=%d perq=%d pts=%d+%d B=%lld precise=%d grid=%d\n", p.num_mid, perq_layer, s0.n, s1.n, (long long)B, (int)precise, grid);
+        fprintf(stderr, "p2s waitstats: pass num_mid=%d perq=%d pts=%d+%d B=%lld precise=%d grid=%d\n", s.num_mid, perq_layer, s0.n, s1.n, (long long)B, (int)precise, grid);
         for (int r = 0; r < 6; ++r) {
             const double tot = (double)h[r * WS_SLOTS + WS_TOTAL];
             if (tot <= 0) continue;
@@ -849,9 +784,9 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
         P2S_CUDA(cudaEventRecord(e1, st));
         t.prof_events.emplace_back(e0, e1);
         // algorithmic FLOPs of this launch: real (un-padded) points, un-duplicated layers
-        double mac_pt = (stash_in ? 0.0 : 3.0 * 64) + 128.0 * 1024;      // layers this launch evaluates
+        double mac_pt = 3.0 * 64 + 128.0 * 1024;
         int prev = 64;
-        for (int l = 0; l < p.num_mid; ++l) { mac_pt += (double)prev * p.mid_N[l]; prev = p.mid_N[l]; }
+        for (int l = 0; l < s.num_mid; ++l) { mac_pt += (double)prev * s.mid_N[l]; prev = s.mid_N[l]; }
         t.prof_flops += 2.0 * mac_pt * (double)(s0.n + s1.n) * (double)B;
     }
 }
@@ -988,9 +923,7 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
                             float* logits, cudaStream_t st, bool precise) {
     TcWeights& t = *m.tc;
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
-    static int64_t bc_env = -1;
-    if (bc_env < 0) { const char* e = getenv("P2S_TC_BCMAX"); bc_env = e ? atoll(e) : 8192; if (bc_env < 256 || bc_env > 65536) bc_env = 8192; }
-    const int64_t Bc_max = bc_env;     // queries per round of pass-kernel launches
+    const int64_t Bc_max = 8192;
     // workspace (floats per query)
     const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 4096 /* 16 KB perq image (hi | lo) */ + 16;
     float* base = m.ws_net.as<float>(per_q * (size_t)Bc_max + 1024);
@@ -1001,16 +934,6 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
     float* fmax_l = take(1024); float* fmax_g = take(1024); float* cat = take(1024); float* h3 = take(256); float* h4 = take(128);
     uint8_t* perq = reinterpret_cast<uint8_t*>(take(4096));
     const bool fc_tc = t.fc_on_tc || precise;   // the precise path needs the split-precision FC kernel's image output
-    // conv0b stash: the STN pass stores the activations behind conv0b (fp16, 128 B per point), the final pass starts from them
-    // instead of re-evaluating conv0a and conv0b (one stage less in its latency-bound mid-layer chain)
-    int tc_opt = 0x7fffffff;
-    { const char* e = getenv("P2S_TC_OPT"); if (e) tc_opt = atoi(e); }
-    const bool use_stash = !precise && (tc_opt & 2);
-    uint8_t* stash = nullptr;
-    if (use_stash) {
-        const size_t tiles = (size_t)std::max((P + kTile - 1) / kTile, (S + kTile - 1) / kTile);
-        stash = reinterpret_cast<uint8_t*>(m.ws_stash.get((size_t)Bc_max * tiles * kTile * 128));
-    }
 
     for (int64_t b0 = 0; b0 < B; b0 += Bc_max) {
         const int64_t Bc = (B - b0 < Bc_max) ? (B - b0) : Bc_max;
@@ -1035,7 +958,7 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
             const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st, precise, stash, nullptr); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st, precise); }
             if (fc_tc) {
                 // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
                 StageScope ts("net: fc tails", st);
@@ -1051,7 +974,7 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
             }
             (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st, precise, nullptr, stash); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st, precise); }
             launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);

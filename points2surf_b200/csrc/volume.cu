@@ -29,10 +29,9 @@ __global__ void sdf_from_logits_kernel(const float* __restrict__ logits, const f
 
 
 struct Ctrl {
-    unsigned long long cntS0;   // zero count of the initial sign volume
-    long long dN[3];            // per-iteration change of the vote's zero count   (rotating, see propagate_kernel)
-    long long dS[3];            // per-iteration change of the sign volume's zero count
-    unsigned listCount[3];      // rotating tile work lists
+    // every counter that many CTAs update in the same iteration sits on its own 128-byte line (same-line atomics serialise in L2)
+    struct alignas(128) Slot { long long dN, dS; unsigned listCount; unsigned pad[27]; unsigned cursor; } slot[3];   // rotating per-iteration accumulators / work-list sizes
+    alignas(128) unsigned long long cntS0;   // zero count of the initial sign volume
     int iters;                  // applied iterations (result)
     int final_buf;              // which ping-pong buffer holds the final signs (result)
     int error;                  // 1: iteration cap hit
@@ -87,7 +86,7 @@ __global__ void init_sign_kernel(float* __restrict__ vol, int res, uint8_t* __re
 __global__ void init_tiles_kernel(int* __restrict__ list0, int* __restrict__ voteZeros, int numTiles, Ctrl* c) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < numTiles) { list0[t] = t; voteZeros[t] = 0; }
-    if (t == 0) c->listCount[0] = (unsigned)numTiles;
+    if (t == 0) c->slot[0].listCount = (unsigned)numTiles;
 }
 
 // ---- iterative sign propagation (sdf.py:156-178) as ONE persistent cooperative kernel -----------------------------------
@@ -108,14 +107,16 @@ struct PropParams {
     uint8_t* flags[2];
     int* voteZeros;
     Ctrl* ctrl;
-    int res, lo, hi, ntx, nty, ntz, maxIters, words;
+    int res, lo, hi, ntx, nty, ntz, maxIters, words, fast;
     float thr;
 };
 
+// SIGMA5 = true: the reference's default sigma (lo = -2, hi = 2) with every loop bound a compile-time constant
+template <bool SIGMA5>
 __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) uint8_t smem[];
-    const int res = p.res, hl = -p.lo, hh = p.hi, W = hl + hh + 1;
+    const int res = p.res, hl = SIGMA5 ? 2 : -p.lo, hh = SIGMA5 ? 2 : p.hi, W = hl + hh + 1;
     const int X0 = TX + hl + hh, Y0 = TY + hl + hh, Z0 = TZ + hl + hh;
     const int HW = (max(hl, hh) + 3) >> 2, WPR = TZ / 4 + 2 * HW;     // halo words per side, words per row
     const int ZS = 4 * WPR, zoff = 4 * HW - hl;                        // row stride in bytes; smem byte zoff <-> z = bz - hl
@@ -123,10 +124,17 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
     int8_t* t1 = (int8_t*)(smem + ((X0 * Y0 * ZS + 15) & ~15));         // [X0][Y0][TZ] z sums (|.| <= 11)
     int16_t* t2 = (int16_t*)((uint8_t*)t1 + ((X0 * Y0 * TZ + 15) & ~15));   // [X0][TY][TZ] zy sums (|.| <= 121)
     __shared__ int sh[8];   // 0 dS, 1 voteZeros, 2..7 changed bbox (min x,y,z, max x,y,z)
+    __shared__ int sh_count, sh_k;
+    __shared__ uint16_t rowxy[(TX + 10) * (TY + 10)];   // halo row -> (x << 8) | y
+    __shared__ long long sh_d[2];
     const int tid = threadIdx.x;
+    for (int r = tid; r < X0 * Y0; r += kPropThreads) rowxy[r] = (uint16_t)(((r / Y0) << 8) | (r % Y0));
+    const int ithr = p.thr > 0.f ? (int)ceilf(p.thr) : 0;               // |n| < thr  <=>  |n| < ceil(thr) for integer n
     long long totalN = 0;                                               // zero count of the vote (whole volume)
     long long totalS = (long long)__ldcg(&p.ctrl->cntS0);               // zero count of the signs
     int iters = 0, final_buf = 0, error = 0;
+    long long ctaN = 0, ctaS = 0;                                        // thread 0: this CTA's share of the iteration's counter changes
+    unsigned long long ctaVisits = 0;
     auto now_ns = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     const bool diag = blockIdx.x == 0 && tid == 0;
     const unsigned long long t_begin = diag ? now_ns() : 0ull;
@@ -136,125 +144,252 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
         if (totalS == 0) { final_buf = it & 1; break; }                 // `if unknown_before.sum() == 0: break`
         if (it >= p.maxIters) { final_buf = it & 1; error = 1; break; }
         if (blockIdx.x == 0 && tid == 0) {                              // recycle the accumulators of iteration it+1 / it+2
-            p.ctrl->dN[nxt] = 0; p.ctrl->dS[nxt] = 0; p.ctrl->listCount[(it + 2) % 3] = 0;
+            p.ctrl->slot[nxt].dN = 0; p.ctrl->slot[nxt].dS = 0; p.ctrl->slot[(it + 2) % 3].listCount = 0; p.ctrl->slot[(it + 2) % 3].cursor = 0;
         }
         // (selects instead of indexing the parameter struct: a runtime index would spill it to local memory)
         const uint8_t* __restrict__ in = (it & 1) ? p.buf[1] : p.buf[0];
         uint8_t* __restrict__ out = (it & 1) ? p.buf[0] : p.buf[1];
-        const int count = (int)__ldcg(&p.ctrl->listCount[cur]);
+        // one reader per CTA; tiles are handed out dynamically (a static stride left CTAs waiting ~30 % of the time at the
+        // barrier): thread 0 draws the next list position while the current tile is being evaluated
+        if (tid == 0) { sh_count = (int)__ldcg(&p.ctrl->slot[cur].listCount); sh_k = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u); }
+        __syncthreads();
+        const int count = sh_count;
         const int* list = cur == 0 ? p.list[0] : (cur == 1 ? p.list[1] : p.list[2]);
         int* listNext = nxt == 0 ? p.list[0] : (nxt == 1 ? p.list[1] : p.list[2]);
         uint8_t* flagCur = (it & 1) ? p.flags[1] : p.flags[0];
         uint8_t* flagNext = (it & 1) ? p.flags[0] : p.flags[1];
-        for (int k = blockIdx.x; k < count; k += gridDim.x) {
+        for (int k = sh_k; k < count; k = sh_k) {
+            int knext = 0;
+            if (tid == 0) knext = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u);   // consumed at the bottom of the loop
             const int tile = __ldcg(&list[k]);
             const int tz = tile % p.ntz, ty = (tile / p.ntz) % p.nty, tx = tile / (p.ntz * p.nty);
             const int bx = tx * TX, by = ty * TY, bz = tz * TZ;
             if (tid < 8) sh[tid] = tid < 2 ? 0 : (tid < 5 ? 1 << 20 : -1);
-            if (tid == 0) { flagCur[tile] = 0; atomicAdd(&p.ctrl->visits, 1ull); }
-            // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration, L1 may
-            // hold stale lines.  Rows are fetched as aligned 32-bit words, four independent loads in flight per thread (a byte
-            // per load made the kernel latency-bound at ~0.4 TB/s); resolutions that are not a multiple of 4 take byte loads.
-            if (p.words) {
-                const int total = X0 * Y0 * WPR, zw0 = (bz >> 2) - HW, lastw = (res >> 2) - 1;
-                uint32_t* s0w = reinterpret_cast<uint32_t*>(s0);
-                for (int base = 0; base < total; base += 4 * kPropThreads) {
-                    uint32_t w[4];
-                    int gz[4];
+            if (tid == 0) flagCur[tile] = 0;
+            if (SIGMA5 || p.fast) {
+                // ---- fast path (word-aligned rows, sigma <= 5): four voxels per 32-bit word everywhere.  Signs are held BIASED
+                // (sign + 1 in {0,1,2}) so that plain integer adds on packed words are exact box sums: no byte ever exceeds
+                // 2 * 5^3 = 250, so nothing carries into its neighbour.  (The byte-at-a-time version spent ~24 k warp
+                // instructions per tile, 60 per z-sum output, and was issue-bound at 9 ms per 256^3 volume.)
+                uint32_t* sb = reinterpret_cast<uint32_t*>(smem);                 // [X0*Y0][WPR] biased signs, tile + halo
+                uint32_t* sraw = sb + X0 * Y0 * WPR;                               // [TX*TY][8]   raw bytes (sign | U0) of the tile
+                uint32_t* t1w = sraw + TX * TY * 8;                                // [X0*Y0][8]   sums along z
+                uint32_t* t2w = t1w + X0 * Y0 * 8;                                 // [X0*TY][8]   sums along z, y
+                const int zw0 = (bz >> 2) - HW, lastw = (res >> 2) - 1, rows = X0 * Y0;
+                const int lane16 = tid & 15, rsub = tid >> 4;                     // 16 lanes per row, 16 rows per pass
+                // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these words in the previous iteration.
+                // Row -> (x, y) comes from a table built once per kernel (two runtime divisions per word made this phase half
+                // of the kernel's instructions); offsets are 32-bit (res^3 <= 2^30).
+                for (int r0 = 0; r0 < rows; r0 += 64) {
+                    uint32_t v[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = base + k * kPropThreads + tid;
-                        w[k] = 0; gz[k] = 0;
-                        if (i < total) {
-                            const int row = i / WPR, wi = i - row * WPR, x = row / Y0, y = row - x * Y0;
-                            const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1);
-                            gz[k] = zw0 + wi;
-                            w[k] = __ldcg(reinterpret_cast<const uint32_t*>(in + ((size_t)gx * res + gy) * res) + min(max(gz[k], 0), lastw));
+                    for (int u = 0; u < 4; ++u) {                                 // four independent loads in flight
+                        const int row = r0 + 16 * u + rsub;
+                        v[u] = 0;
+                        if (row < rows && lane16 < WPR) {
+                            const unsigned xy = rowxy[row];
+                            const int gx = min(max(bx + (int)(xy >> 8) - hl, 0), res - 1), gy = min(max(by + (int)(xy & 0xffu) - hl, 0), res - 1);
+                            const unsigned wofs = (unsigned)(gx * res + gy) * (unsigned)(res >> 2) + (unsigned)min(max(zw0 + lane16, 0), lastw);
+                            v[u] = __ldcg(reinterpret_cast<const uint32_t*>(in) + wofs);
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = base + k * kPropThreads + tid;
-                        if (i < total) {
-                            uint32_t v = w[k];
-                            if (gz[k] < 0) v = (v & 0xffu) * 0x01010101u;            // left of the volume: first voxel of the row
-                            else if (gz[k] > lastw) v = (v >> 24) * 0x01010101u;     // right of it: last voxel
-                            s0w[i] = v;
+                    for (int u = 0; u < 4; ++u) {
+                        const int row = r0 + 16 * u + rsub;
+                        if (row < rows && lane16 < WPR) {
+                            const int gzw = zw0 + lane16;
+                            uint32_t raw = v[u];
+                            if (gzw < 0) raw = (raw & 0xffu) * 0x01010101u;           // left of the volume: first voxel of the row
+                            else if (gzw > lastw) raw = (raw >> 24) * 0x01010101u;    // right of it: last voxel
+                            sb[row * WPR + lane16] = ((raw & 0x03030303u) + 0x01010101u) & 0x03030303u;   // 2-bit sign -> sign + 1
+                            const unsigned xy = rowxy[row];
+                            const unsigned xi = (xy >> 8) - (unsigned)hl, yi = (xy & 0xffu) - (unsigned)hl, wi = (unsigned)(lane16 - HW);
+                            if (xi < (unsigned)TX && yi < (unsigned)TY && wi < 8u) sraw[(xi * TY + yi) * 8 + wi] = raw;
                         }
                     }
+                }
+                __syncthreads();
+                {   // sums along z: output word j of a row = sum over t of the word starting at byte zoff + 4 j + t
+                    const int s = zoff & 3, jb0 = zoff >> 2;
+                    for (int i = tid; i < rows * 8; i += kPropThreads) {
+                        const int row = i >> 3, j = (i & 7) + jb0;
+                        const uint32_t* r = sb + row * WPR + j;
+                        const uint32_t w0 = r[0], w1 = (j + 1 < WPR) ? r[1] : 0u, w2 = (j + 2 < WPR) ? r[2] : 0u;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int t = 0; t < W; ++t) {
+                            const int k = s + t;
+                            acc += __funnelshift_r(k < 4 ? w0 : w1, k < 4 ? w1 : w2, (k & 3) * 8);
+                        }
+                        t1w[i] = acc;
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < X0 * TY * 8; i += kPropThreads) {            // sums along y
+                    const int j = i & 7, y = (i >> 3) & (TY - 1), x = i >> 6;
+                    const uint32_t* r = t1w + ((x * Y0 + y) << 3) + j;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int t = 0; t < W; ++t) acc += r[t << 3];
+                    t2w[i] = acc;
+                }
+                __syncthreads();
+                {   // sums along x, threshold, apply
+                    const int bias = W * W * W;                                 // every tap carries +1
+                    int dS = 0, nz = 0, mnx = 1 << 20, mxx = -1, mny = 1 << 20, mxy = -1, mnz = 1 << 20, mxz = -1;
+                    for (int i = tid; i < TX * TY * 8; i += kPropThreads) {
+                        const int j = i & 7, y = (i >> 3) & (TY - 1), x = i >> 6;
+                        const int gx = bx + x, gy = by + y, gzw = (bz >> 2) + j;
+                        if (gx >= res || gy >= res || gzw > lastw) continue;
+                        const uint32_t* r = t2w + ((x * TY + y) << 3) + j;
+                        uint32_t sum = 0;
+#pragma unroll
+                        for (int t = 0; t < W; ++t) sum += r[(t * TY) << 3];
+                        const uint32_t raw = sraw[i];
+                        uint32_t cand = 0;                                        // the four votes as sign bytes with the U0 flag
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int n = (int)((sum >> (8 * q)) & 0xffu) - bias;
+                            const int vote = (abs(n) < ithr || n == 0) ? 0 : (n > 0 ? 1 : 3);      // 2-bit two's complement
+                            nz += (vote == 0);
+                            cand |= (uint32_t)(vote | kU0) << (8 * q);
+                        }
+                        const uint32_t um = ((raw >> 2) & 0x01010101u) * 0xffu;     // 0xff in the bytes that were unknown at the start
+                        const uint32_t neww = (raw & ~um) | (cand & um);
+                        reinterpret_cast<uint32_t*>(out)[(unsigned)(gx * res + gy) * (unsigned)(res >> 2) + (unsigned)gzw] = neww;
+                        const uint32_t diff = neww ^ raw;
+                        if (diff) {                                               // rare: signs change only along the front
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if ((diff >> (8 * q)) & 0xffu) {
+                                    dS += (int)(((neww >> (8 * q)) & 3u) == 0u) - (int)(((raw >> (8 * q)) & 3u) == 0u);
+                                    const int z = 4 * j + q;
+                                    mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y); mnz = min(mnz, z); mxz = max(mxz, z);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { dS += __shfl_xor_sync(0xffffffffu, dS, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
+                    if (__any_sync(0xffffffffu, mxx >= 0)) {                       // one set of shared atomics per warp, not per voxel
+                        mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+                        mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+                        mnz = __reduce_min_sync(0xffffffffu, mnz); mxz = __reduce_max_sync(0xffffffffu, mxz);
+                        if ((tid & 31) == 0) {
+                            atomicMin(&sh[2], mnx); atomicMax(&sh[5], mxx); atomicMin(&sh[3], mny); atomicMax(&sh[6], mxy);
+                            atomicMin(&sh[4], mnz); atomicMax(&sh[7], mxz);
+                        }
+                    }
+                    if ((tid & 31) == 0) { if (dS) atomicAdd(&sh[0], dS); if (nz) atomicAdd(&sh[1], nz); }
                 }
             } else {
-                for (int i = tid; i < X0 * Y0 * Z0; i += kPropThreads) {
-                    const int z = i % Z0, xy = i / Z0, y = xy % Y0, x = xy / Y0;
-                    const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1), gz = min(max(bz + z - hl, 0), res - 1);
-                    s0[xy * ZS + zoff + z] = __ldcg(in + ((size_t)gx * res + gy) * res + gz);
-                }
-            }
-            __syncthreads();
-            for (int i = tid; i < X0 * Y0 * TZ; i += kPropThreads) {       // sum along z
-                const int z = i & (TZ - 1), xy = i >> 5;
-                const uint8_t* r = s0 + xy * ZS + zoff + z;
-                int acc = 0;
-                for (int t = 0; t < W; ++t) acc += sign_of(r[t]);
-                t1[i] = (int8_t)acc;
-            }
-            __syncthreads();
-            for (int i = tid; i < X0 * TZ; i += kPropThreads) {            // sum along y, sliding window
-                const int z = i & (TZ - 1), x = i >> 5;
-                const int8_t* r = t1 + (x * Y0) * TZ + z;
-                int acc = 0;
-                for (int t = 0; t < W; ++t) acc += r[t * TZ];
-                t2[(x * TY) * TZ + z] = (int16_t)acc;
-                for (int y = 1; y < TY; ++y) {
-                    acc += r[(y + W - 1) * TZ] - r[(y - 1) * TZ];
-                    t2[(x * TY + y) * TZ + z] = (int16_t)acc;
-                }
-            }
-            __syncthreads();
-            {                                                              // sum along x, threshold, apply
-                const int z = tid & (TZ - 1), y = tid >> 5;
-                const int gy = by + y, gz = bz + z;
-                const bool col_ok = gy < res && gz < res;
-                const int16_t* r = t2 + y * TZ + z;
-                int acc = 0;
-                for (int t = 0; t < W; ++t) acc += r[t * TY * TZ];
-                int dS = 0, nz = 0, cminx = 1 << 20, cmaxx = -1;
-                for (int x = 0; x < TX; ++x) {
-                    if (x > 0) acc += r[(x + W - 1) * TY * TZ] - r[(x - 1) * TY * TZ];
-                    const int gx = bx + x;
-                    if (col_ok && gx < res) {
-                        int vote = 0;
-                        if (!(fabsf((float)acc) < p.thr)) vote = acc > 0 ? 1 : (acc < 0 ? -1 : 0);
-                        nz += (vote == 0);
-                        const uint8_t b = s0[((x + hl) * Y0 + (y + hl)) * ZS + zoff + hl + z];
-                        uint8_t nb = b;
-                        if (b & kU0) {
-                            const int so = sign_of(b);
-                            nb = (uint8_t)((vote & 3) | kU0);
-                            if (vote != so) { dS += (vote == 0) - (so == 0); cminx = min(cminx, x); cmaxx = max(cmaxx, x); }
+                // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration, L1 may
+                // hold stale lines.  Rows are fetched as aligned 32-bit words, four independent loads in flight per thread (a byte
+                // per load made the kernel latency-bound at ~0.4 TB/s); resolutions that are not a multiple of 4 take byte loads.
+                if (p.words) {
+                    const int total = X0 * Y0 * WPR, zw0 = (bz >> 2) - HW, lastw = (res >> 2) - 1;
+                    uint32_t* s0w = reinterpret_cast<uint32_t*>(s0);
+                    for (int base = 0; base < total; base += 4 * kPropThreads) {
+                        uint32_t w[4];
+                        int gz[4];
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = base + k * kPropThreads + tid;
+                            w[k] = 0; gz[k] = 0;
+                            if (i < total) {
+                                const int row = i / WPR, wi = i - row * WPR, x = row / Y0, y = row - x * Y0;
+                                const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1);
+                                gz[k] = zw0 + wi;
+                                w[k] = __ldcg(reinterpret_cast<const uint32_t*>(in + ((size_t)gx * res + gy) * res) + min(max(gz[k], 0), lastw));
+                            }
                         }
-                        out[((size_t)gx * res + gy) * res + gz] = nb;
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = base + k * kPropThreads + tid;
+                            if (i < total) {
+                                uint32_t v = w[k];
+                                if (gz[k] < 0) v = (v & 0xffu) * 0x01010101u;            // left of the volume: first voxel of the row
+                                else if (gz[k] > lastw) v = (v >> 24) * 0x01010101u;     // right of it: last voxel
+                                s0w[i] = v;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = tid; i < X0 * Y0 * Z0; i += kPropThreads) {
+                        const int z = i % Z0, xy = i / Z0, y = xy % Y0, x = xy / Y0;
+                        const int gx = min(max(bx + x - hl, 0), res - 1), gy = min(max(by + y - hl, 0), res - 1), gz = min(max(bz + z - hl, 0), res - 1);
+                        s0[xy * ZS + zoff + z] = __ldcg(in + ((size_t)gx * res + gy) * res + gz);
                     }
                 }
-                // block totals
-                unsigned ch = __ballot_sync(0xffffffffu, cmaxx >= 0);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { dS += __shfl_xor_sync(0xffffffffu, dS, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
-                if ((tid & 31) == 0) { if (dS) atomicAdd(&sh[0], dS); if (nz) atomicAdd(&sh[1], nz); }
-                if (ch) {                                                  // rare: signs change only along the front
-                    if (cmaxx >= 0) {
-                        atomicMin(&sh[2], cminx); atomicMax(&sh[5], cmaxx);
-                        atomicMin(&sh[3], y); atomicMax(&sh[6], y);
-                        atomicMin(&sh[4], z); atomicMax(&sh[7], z);
+                __syncthreads();
+                for (int i = tid; i < X0 * Y0 * TZ; i += kPropThreads) {       // sum along z
+                    const int z = i & (TZ - 1), xy = i >> 5;
+                    const uint8_t* r = s0 + xy * ZS + zoff + z;
+                    int acc = 0;
+                    for (int t = 0; t < W; ++t) acc += sign_of(r[t]);
+                    t1[i] = (int8_t)acc;
+                }
+                __syncthreads();
+                for (int i = tid; i < X0 * TZ; i += kPropThreads) {            // sum along y, sliding window
+                    const int z = i & (TZ - 1), x = i >> 5;
+                    const int8_t* r = t1 + (x * Y0) * TZ + z;
+                    int acc = 0;
+                    for (int t = 0; t < W; ++t) acc += r[t * TZ];
+                    t2[(x * TY) * TZ + z] = (int16_t)acc;
+                    for (int y = 1; y < TY; ++y) {
+                        acc += r[(y + W - 1) * TZ] - r[(y - 1) * TZ];
+                        t2[(x * TY + y) * TZ + z] = (int16_t)acc;
+                    }
+                }
+                __syncthreads();
+                {                                                              // sum along x, threshold, apply
+                    const int z = tid & (TZ - 1), y = tid >> 5;
+                    const int gy = by + y, gz = bz + z;
+                    const bool col_ok = gy < res && gz < res;
+                    const int16_t* r = t2 + y * TZ + z;
+                    int acc = 0;
+                    for (int t = 0; t < W; ++t) acc += r[t * TY * TZ];
+                    int dS = 0, nz = 0, cminx = 1 << 20, cmaxx = -1;
+                    for (int x = 0; x < TX; ++x) {
+                        if (x > 0) acc += r[(x + W - 1) * TY * TZ] - r[(x - 1) * TY * TZ];
+                        const int gx = bx + x;
+                        if (col_ok && gx < res) {
+                            int vote = 0;
+                            if (!(fabsf((float)acc) < p.thr)) vote = acc > 0 ? 1 : (acc < 0 ? -1 : 0);
+                            nz += (vote == 0);
+                            const uint8_t b = s0[((x + hl) * Y0 + (y + hl)) * ZS + zoff + hl + z];
+                            uint8_t nb = b;
+                            if (b & kU0) {
+                                const int so = sign_of(b);
+                                nb = (uint8_t)((vote & 3) | kU0);
+                                if (vote != so) { dS += (vote == 0) - (so == 0); cminx = min(cminx, x); cmaxx = max(cmaxx, x); }
+                            }
+                            out[((size_t)gx * res + gy) * res + gz] = nb;
+                        }
+                    }
+                    // block totals
+                    unsigned ch = __ballot_sync(0xffffffffu, cmaxx >= 0);
+    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { dS += __shfl_xor_sync(0xffffffffu, dS, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
+                    if ((tid & 31) == 0) { if (dS) atomicAdd(&sh[0], dS); if (nz) atomicAdd(&sh[1], nz); }
+                    if (ch) {                                                  // rare: signs change only along the front
+                        if (cmaxx >= 0) {
+                            atomicMin(&sh[2], cminx); atomicMax(&sh[5], cmaxx);
+                            atomicMin(&sh[3], y); atomicMax(&sh[6], y);
+                            atomicMin(&sh[4], z); atomicMax(&sh[7], z);
+                        }
                     }
                 }
             }
             __syncthreads();
-            if (tid == 0) {
+            if (tid == 0) {     // this CTA's contribution to the iteration's counters: one pair of atomics per iteration, below
                 const int old = __ldcg(&p.voteZeros[tile]);
-                if (sh[1] != old) { p.voteZeros[tile] = sh[1]; atomicAdd((unsigned long long*)&p.ctrl->dN[cur], (unsigned long long)(long long)(sh[1] - old)); }
-                if (sh[0]) atomicAdd((unsigned long long*)&p.ctrl->dS[cur], (unsigned long long)(long long)sh[0]);
+                if (sh[1] != old) { p.voteZeros[tile] = sh[1]; ctaN += sh[1] - old; }
+                ctaS += sh[0];
+                ++ctaVisits;
             }
+            bool fresh = false;
+            int nfresh = 0;
             if (sh[5] >= 0 && tid < 27) {
                 // a changed sign at local c moves the votes at c-hh .. c+hl: neighbours whose voxels fall in that range
                 const int dz = tid % 3 - 1, dy = (tid / 3) % 3 - 1, dx = tid / 9 - 1;
@@ -267,20 +402,40 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                     // byte flags, word-wide atomic: set our byte, see whether it was clear
                     unsigned* wptr = (unsigned*)(flagNext + (n & ~3));
                     const unsigned bit = 1u << (8 * (n & 3));
-                    if (!(atomicOr(wptr, bit) & bit)) listNext[atomicAdd(&p.ctrl->listCount[nxt], 1u)] = n;
+                    fresh = !(atomicOr(wptr, bit) & bit);
+                    nfresh = n;
                 }
             }
+            if (tid < 32) {          // (the 27 marking threads are lanes of warp 0) one list-size atomic per tile, not per neighbour
+                const unsigned m = __ballot_sync(0xffffffffu, fresh);
+                if (m) {
+                    unsigned basepos = 0;
+                    if (tid == 0) basepos = atomicAdd(&p.ctrl->slot[nxt].listCount, (unsigned)__popc(m));
+                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                    if (fresh) listNext[basepos + __popc(m & ((1u << tid) - 1u))] = nfresh;
+                }
+            }
+            __syncthreads();                     // every thread has read sh_k (= k) and sh[]
+            if (tid == 0) sh_k = knext;
             __syncthreads();
+        }
+        if (tid == 0) {
+            if (ctaN) atomicAdd((unsigned long long*)&p.ctrl->slot[cur].dN, (unsigned long long)ctaN);
+            if (ctaS) atomicAdd((unsigned long long*)&p.ctrl->slot[cur].dS, (unsigned long long)ctaS);
+            ctaN = 0; ctaS = 0;
         }
         const unsigned long long ts = diag ? now_ns() : 0ull;
         grid.sync();
         if (diag) { t_sync += now_ns() - ts; if (it == 0) p.ctrl->t_first = now_ns() - t_begin; }
-        totalN += __ldcg(&p.ctrl->dN[cur]);
-        const long long afterS = totalS + __ldcg(&p.ctrl->dS[cur]);
+        if (tid == 0) { sh_d[0] = __ldcg(&p.ctrl->slot[cur].dN); sh_d[1] = __ldcg(&p.ctrl->slot[cur].dS); }
+        __syncthreads();
+        totalN += sh_d[0];
+        const long long afterS = totalS + sh_d[1];
         if (totalN >= totalS) { final_buf = it & 1; break; }            // `if unknown_after.sum() >= unknown_before.sum(): break`
         totalS = afterS;
         ++iters;
     }
+    if (tid == 0 && ctaVisits) atomicAdd(&p.ctrl->visits, ctaVisits);
     if (blockIdx.x == 0 && tid == 0) { p.ctrl->iters = iters; p.ctrl->final_buf = final_buf; p.ctrl->error = error; p.ctrl->t_total = now_ns() - t_begin; p.ctrl->t_sync = t_sync; }
 }
 
@@ -329,7 +484,7 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     pp.maxIters = 64 * res;
     const int numTiles = pp.ntx * pp.nty * pp.ntz;
     const size_t nt4 = ((size_t)numTiles + 3) & ~(size_t)3;
-    size_t off = 256;
+    size_t off = (sizeof(Ctrl) + 255) & ~(size_t)255;
     const size_t off_A = off; off += (V + 255) & ~(size_t)255;
     const size_t off_B = off; off += (V + 255) & ~(size_t)255;
     const size_t off_lists = off; off += 3 * nt4 * sizeof(int);
@@ -359,16 +514,22 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     const int HW = (std::max(hl, hh) + 3) / 4, ZS = TZ + 8 * HW;
     (void)Z0;
     pp.words = (res % 4 == 0) ? 1 : 0;       // aligned 32-bit row loads need word-aligned rows
-    const size_t smem = (size_t)((X0 * Y0 * ZS + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
+    pp.fast = (pp.words && sigma <= 5) ? 1 : 0;   // packed biased-byte sums need 2 * sigma^3 <= 255
+    const size_t smem_generic = (size_t)((X0 * Y0 * ZS + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
+    const size_t smem_fast = 4 * ((size_t)X0 * Y0 * (ZS / 4) + (size_t)TX * TY * 8 + (size_t)X0 * Y0 * 8 + (size_t)X0 * TY * 8);
+    const size_t smem = pp.fast ? smem_fast : smem_generic;
     int dev_id = 0, sms = 148, per_sm = 0;
     P2S_CUDA(cudaGetDevice(&dev_id));
     P2S_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
-    P2S_CUDA(cudaFuncSetAttribute(propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel, kPropThreads, smem));
+    const bool s5 = pp.fast && sigma == 5;
+    const void* kfn = s5 ? (const void*)propagate_kernel<true> : (const void*)propagate_kernel<false>;
+    P2S_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (s5) P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<true>, kPropThreads, smem));
+    else P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<false>, kPropThreads, smem));
     P2S_CHECK(per_sm >= 1, "sign propagation kernel does not fit on an SM");
     const unsigned grid = (unsigned)std::max(1, std::min(numTiles, sms * per_sm));
     void* args[] = {&pp};
-    P2S_CUDA(cudaLaunchCooperativeKernel((const void*)propagate_kernel, dim3(grid), dim3(kPropThreads), args, smem, st));
+    P2S_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kPropThreads), args, smem, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     P2S_LAUNCH(finalize_kernel, blocks, 256, 0, st, vol, pp.buf[0], pp.buf[1], ctrl, V);
     Ctrl h{};
