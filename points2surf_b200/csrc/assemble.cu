@@ -100,7 +100,11 @@ __device__ void find_boundary(SelectSmemT<CAP>& s, int N, int k, int cand_cap, K
     }
 }
 
-// bitonic sort of (key, id) ascending over the first P = pow2ceil(n) slots (slots >= n are padded with +inf keys)
+// bitonic sort of (key, id) ascending over the first P = pow2ceil(n) slots (slots >= n are padded with +inf keys).
+// The total order (key, id) is strict, so the result does not depend on the network used.
+// P <= 512: two elements per thread live in registers; compare-exchanges at element strides 1 (in-thread) and 2..32 (warp
+// shuffles) need no barrier, only the strides >= 64 go through shared memory: 10 block barriers per sort instead of 45
+// (the barriers, not the instructions, were what the kNN kernel spent its time on).
 template <int CAP>
 __device__ void sort_candidates(SelectSmemT<CAP>& s, int n) {
     const int tid = threadIdx.x;
@@ -109,19 +113,63 @@ __device__ void sort_candidates(SelectSmemT<CAP>& s, int n) {
     for (int i = tid; i < P; i += kThreads)
         if (i >= n) { s.cand_key[i] = ~0ull; s.cand_id[i] = 0x7fffffff; }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < P / 2; t += kThreads) {
-                int lo = 2 * t - (t & (stride - 1));
-                int hi = lo + stride;
-                bool up = ((lo & size) == 0);
-                unsigned long long ka = s.cand_key[lo], kb = s.cand_key[hi];
-                int ia = s.cand_id[lo], ib = s.cand_id[hi];
-                bool gt = (ka > kb) || (ka == kb && ia > ib);
-                if (gt == up) { s.cand_key[lo] = kb; s.cand_key[hi] = ka; s.cand_id[lo] = ib; s.cand_id[hi] = ia; }
+    auto smem_stage = [&](int size, int stride) {
+        for (int t = tid; t < P / 2; t += kThreads) {
+            int lo = 2 * t - (t & (stride - 1));
+            int hi = lo + stride;
+            bool up = ((lo & size) == 0);
+            unsigned long long ka = s.cand_key[lo], kb = s.cand_key[hi];
+            int ia = s.cand_id[lo], ib = s.cand_id[hi];
+            bool gt = (ka > kb) || (ka == kb && ia > ib);
+            if (gt == up) { s.cand_key[lo] = kb; s.cand_key[hi] = ka; s.cand_id[lo] = ib; s.cand_id[hi] = ia; }
+        }
+        __syncthreads();
+    };
+    if (P <= 2 * kThreads) {
+        static_assert(kThreads == 256, "register sort assumes 256 threads (2 elements per thread at P = 512)");
+        const bool active = 2 * tid < P;          // warp-uniform: P is a multiple of 64
+        unsigned long long k0 = 0, k1 = 0;
+        int i0 = 0, i1 = 0;
+        auto load = [&] { if (active) { k0 = s.cand_key[2 * tid]; k1 = s.cand_key[2 * tid + 1]; i0 = s.cand_id[2 * tid]; i1 = s.cand_id[2 * tid + 1]; } };
+        auto store = [&] { if (active) { s.cand_key[2 * tid] = k0; s.cand_key[2 * tid + 1] = k1; s.cand_id[2 * tid] = i0; s.cand_id[2 * tid + 1] = i1; } };
+        // strides min(size / 2, 32) .. 1 of the merge of `size`, in registers
+        auto reg_stages = [&](int size) {
+            if (!active) return;
+            for (int stride = (size >> 1) < 32 ? (size >> 1) : 32; stride >= 2; stride >>= 1) {
+                const int m = stride >> 1;                              // lane mask of the partner thread
+                const bool up = (((2 * tid) & size) == 0);
+                const bool keep_min = (((2 * tid) & stride) == 0) == up;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    unsigned long long& k = b ? k1 : k0;
+                    int& id = b ? i1 : i0;
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, m);
+                    const int oi = __shfl_xor_sync(0xffffffffu, id, m);
+                    const bool other_less = (ok < k) || (ok == k && oi < id);
+                    if (other_less == keep_min) { k = ok; id = oi; }
+                }
             }
+            {   // stride 1: the thread's own pair
+                const bool up = (((2 * tid) & size) == 0);
+                const bool gt = (k0 > k1) || (k0 == k1 && i0 > i1);
+                if (gt == up) { const unsigned long long tk = k0; k0 = k1; k1 = tk; const int ti = i0; i0 = i1; i1 = ti; }
+            }
+        };
+        load();
+        for (int size = 2; size <= 64 && size <= P; size <<= 1) reg_stages(size);
+        store();
+        __syncthreads();
+        for (int size = 128; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride >= 64; stride >>= 1) smem_stage(size, stride);
+            load();
+            reg_stages(size);
+            store();
             __syncthreads();
         }
+        return;
+    }
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) smem_stage(size, stride);
 }
 
 __device__ __forceinline__ double dist2_f64(const float* __restrict__ pts, int i, double qx, double qy, double qz) {

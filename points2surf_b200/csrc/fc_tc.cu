@@ -55,13 +55,18 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
         // ---- producers: A[m0 + tid][k0 .. k0+31] -> fp16 hi / lo, K-major (LBO 128, SBO 512)
         const int row = m0 + tid;
         const float* src = A + (int64_t)(row < M ? row : 0) * lda;
+        // register double buffer: the loads of k-step kt + 1 are in flight while k-step kt is converted and stored (with one
+        // stage of loads per thread the producers were latency-bound: ~800 cycles of L2 latency per 384 cycles of MMA)
+        float4 v[8], nv[8];
+        const bool row_ok = row < M;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = row_ok ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % kStages;
             const uint32_t use = (uint32_t)(kt / kStages);
-            // issue the global loads before waiting for the slot
-            float4 v[8];
+            const bool more = row_ok && (kt + 1 < nk);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (row < M) ? *reinterpret_cast<const float4*>(src + kt * kBK + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) nv[j] = more ? *reinterpret_cast<const float4*>(src + (kt + 1) * kBK + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait_bounded(&bars->empty[s], (use & 1) ^ 1);
             uint8_t* dst = smem + s * kStageA + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 16u;
 #pragma unroll
@@ -81,6 +86,8 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars->full[s]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = nv[j];
         }
         // ---- epilogue
         mbar_wait_bounded(&bars->d_full, 0);

@@ -86,7 +86,9 @@ struct PassParams {
     int perq_layer;            // index of the mid layer with per-query weights, or -1
     const uint8_t* perq_img;   // [B] x 8192 B (precise: hi | lo, 16384 B)
     const uint8_t* w3_img;     // [8 chunks][32768 B] (precise: [8][hi | lo])  (K-major, LBO 128, SBO 2048)
-    float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer)
+    float* out;                // [B,1024] max over the points + b3, optionally ReLU (max(x) + b = max(x + b): the bias is added once per channel)
+    const float* b3;           // [1024] bias of the big layer
+    int out_relu;
     long long* wstats;         // diagnostics: per-role barrier wait cycles (null = off)
 };
 
@@ -530,7 +532,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) p.out[(size_t)q * 1024 + (part * C::kChunks + c) * 128 + ch_lane] = acc[c];
+            for (int c = 0; c < C::kChunks; ++c) {
+                const int ch = (part * C::kChunks + c) * 128 + ch_lane;
+                float o = acc[c] + __ldg(p.b3 + ch);
+                if (p.out_relu) o = fmaxf(o, 0.f);
+                p.out[(size_t)q * 1024 + ch] = o;
+            }
         }
     }
     if (STATS) ws_flush(p.wstats, warp == 8 ? 0 : (warp == 13 ? 1 : (warp < 4 ? 2 : (warp >= 14 ? 4 : (warp >= 9 ? 3 : 5)))), ws, t_begin);
@@ -725,7 +732,7 @@ uint8_t* pack_w3(TcWeights& t, const Layer& L, bool split = false) {   // 8 chun
 }
 
 void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const float* query, const float* R,
-                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st, bool precise) {
+                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, bool out_relu, cudaStream_t st, bool precise) {
     PassParams p{};
     p.seg[0] = s0; p.seg[1] = s1;
     p.query = query; p.R = R;
@@ -738,6 +745,8 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
     p.perq_img = perq_img;
     p.w3_img = precise ? s.w3_img_p : s.w3_img;
     p.out = out;
+    p.b3 = s.b3;
+    p.out_relu = out_relu ? 1 : 0;
     p.wstats = nullptr;
     TcWeights& t = *m.tc;
     static int wstats_on = -1;
@@ -799,10 +808,8 @@ void run_fc(const TcFc& f, const float* in, int lda, float* out, int ldc, int64_
     else launch_gemm_nt(in, 0, lda, L.W, 0, L.b, out, 0, ldc, (int)Bc, L.cout, L.cin, 1, relu, st);
 }
 
-void fc_tail(const Layer& b3src, const TcStnFc& s, bool on_tc, const float* gmax_raw, int64_t Bc, float* g, float* f1, float* f2, float* out, cudaStream_t st) {
-    // g = relu(max + b3) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
-    P2S_CUDA(cudaMemcpyAsync(g, gmax_raw, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
-    launch_bias_act(g, b3src.b, Bc, 1024, true, st);
+void fc_tail(const TcStnFc& s, bool on_tc, const float* g, int64_t Bc, float* f1, float* f2, float* out, cudaStream_t st) {
+    // g = relu(max + b3) (written by the pass kernel) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
     run_fc(s.fc1, g, 1024, f1, 512, Bc, true, on_tc, st);
     run_fc(s.fc2, f1, 512, f2, 256, Bc, true, on_tc, st);
     run_fc(s.fc3, f2, 256, out, s.fc3.L->cout, Bc, false, on_tc, st);
@@ -943,13 +950,13 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
         const float* Rq = nullptr;
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st, precise); }
-            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, true, st, precise); }
+            { StageScope ts("net: fc tails", st); fc_tail(t.qstn_fc, fc_tc, gmax, Bc, f1, f2, q4, st); }
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
-            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st, precise);
-            fc_tail(m.global.stn1.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st);
+            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, true, st, precise);
+            fc_tail(t.qstn_fc, fc_tc, gmax, Bc, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         }
@@ -958,24 +965,21 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
             const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st, precise); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, true, st, precise); }
             if (fc_tc) {
                 // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
                 StageScope ts("net: fc tails", st);
-                P2S_CUDA(cudaMemcpyAsync(g, gmax, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
-                launch_bias_act(g, f.stn2.c3.b, Bc, 1024, true, st);
-                run_fc(t.stn_fc[br].fc1, g, 1024, f1, 512, Bc, true, true, st);
+                run_fc(t.stn_fc[br].fc1, gmax, 1024, f1, 512, Bc, true, true, st);
                 run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
                 launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
             } else {
-                { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], false, gmax, Bc, g, f1, f2, T, st); }
+                { StageScope ts("net: fc tails", st); fc_tail(t.stn_fc[br], false, gmax, Bc, f1, f2, T, st); }
                 // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
                 { StageScope ts("net: fold W1*T", st); P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq); }
             }
-            (void)Tt;
+            (void)Tt; (void)g;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st, precise); }
-            launch_bias_act(fmax, f.conv3.b, Bc, 1024, false, st);
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, false, st, precise); }
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
         StageScope ts_head("net: fc tails", st);

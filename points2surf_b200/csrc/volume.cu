@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
     int8_t* t1 = (int8_t*)(smem + ((X0 * Y0 * ZS + 15) & ~15));         // [X0][Y0][TZ] z sums (|.| <= 11)
     int16_t* t2 = (int16_t*)((uint8_t*)t1 + ((X0 * Y0 * TZ + 15) & ~15));   // [X0][TY][TZ] zy sums (|.| <= 121)
     __shared__ int sh[8];   // 0 dS, 1 voteZeros, 2..7 changed bbox (min x,y,z, max x,y,z)
-    __shared__ int sh_count, sh_k;
+    __shared__ int sh_count, sh_next[2][2];   // [parity][0: list position, 1: tile] of the tile after the current one
     __shared__ uint16_t rowxy[(TX + 10) * (TY + 10)];   // halo row -> (x << 8) | y
     __shared__ long long sh_d[2];
     const int tid = threadIdx.x;
@@ -151,17 +151,31 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
         uint8_t* __restrict__ out = (it & 1) ? p.buf[0] : p.buf[1];
         // one reader per CTA; tiles are handed out dynamically (a static stride left CTAs waiting ~30 % of the time at the
         // barrier): thread 0 draws the next list position while the current tile is being evaluated
-        if (tid == 0) { sh_count = (int)__ldcg(&p.ctrl->slot[cur].listCount); sh_k = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u); }
+        const int* list = cur == 0 ? p.list[0] : (cur == 1 ? p.list[1] : p.list[2]);
+        if (tid == 0) {
+            const int k0 = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u);
+            const int cnt = (int)__ldcg(&p.ctrl->slot[cur].listCount);
+            sh_count = cnt; sh_next[0][0] = k0; sh_next[0][1] = k0 < cnt ? __ldcg(&list[k0]) : -1;
+        }
         __syncthreads();
         const int count = sh_count;
-        const int* list = cur == 0 ? p.list[0] : (cur == 1 ? p.list[1] : p.list[2]);
         int* listNext = nxt == 0 ? p.list[0] : (nxt == 1 ? p.list[1] : p.list[2]);
         uint8_t* flagCur = (it & 1) ? p.flags[1] : p.flags[0];
         uint8_t* flagNext = (it & 1) ? p.flags[0] : p.flags[1];
-        for (int k = sh_k; k < count; k = sh_k) {
-            int knext = 0;
-            if (tid == 0) knext = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u);   // consumed at the bottom of the loop
-            const int tile = __ldcg(&list[k]);
+        // Per tile the global-memory round trips that used to be exposed one after the other (list entry, three passes of halo
+        // loads, the tile's vote-zero count, the neighbour flags, the list append) are overlapped: thread 0 draws the next list
+        // position first, the halo loads go out in one batch, the next tile id and the old zero count are fetched behind them, and
+        // warp 0 marks the neighbours while the other warps already load the next tile (double-buffered hand-over slot).
+        int par = 0;
+        for (int k = sh_next[0][0]; k < count; k = sh_next[par][0]) {
+            const int tile = sh_next[par][1];
+            int knext = 0, oldvz = 0;
+            if (tid == 0) knext = (int)atomicAdd(&p.ctrl->slot[cur].cursor, 1u);
+            auto prefetch_next = [&] {      // thread 0, right behind the halo loads
+                oldvz = __ldcg(&p.voteZeros[tile]);
+                const int tn = knext < count ? __ldcg(&list[knext]) : -1;
+                sh_next[par ^ 1][0] = knext; sh_next[par ^ 1][1] = tn;
+            };
             const int tz = tile % p.ntz, ty = (tile / p.ntz) % p.nty, tx = tile / (p.ntz * p.nty);
             const int bx = tx * TX, by = ty * TY, bz = tz * TZ;
             if (tid < 8) sh[tid] = tid < 2 ? 0 : (tid < 5 ? 1 << 20 : -1);
@@ -180,10 +194,11 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                 // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these words in the previous iteration.
                 // Row -> (x, y) comes from a table built once per kernel (two runtime divisions per word made this phase half
                 // of the kernel's instructions); offsets are 32-bit (res^3 <= 2^30).
-                for (int r0 = 0; r0 < rows; r0 += 64) {
-                    uint32_t v[4];
+                constexpr int kBatch = SIGMA5 ? 9 : 4;                            // sigma 5: all 144 rows of the tile in ONE batch of loads
+                for (int r0 = 0; r0 < rows; r0 += 16 * kBatch) {
+                    uint32_t v[kBatch];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {                                 // four independent loads in flight
+                    for (int u = 0; u < kBatch; ++u) {                            // independent loads in flight
                         const int row = r0 + 16 * u + rsub;
                         v[u] = 0;
                         if (row < rows && lane16 < WPR) {
@@ -193,8 +208,9 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                             v[u] = __ldcg(reinterpret_cast<const uint32_t*>(in) + wofs);
                         }
                     }
+                    if (tid == 0 && r0 == 0) prefetch_next();
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kBatch; ++u) {
                         const int row = r0 + 16 * u + rsub;
                         if (row < rows && lane16 < WPR) {
                             const int gzw = zw0 + lane16;
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                 // tile + halo, edges replicated ('nearest'); .cg loads: other SMs wrote these bytes in the previous iteration, L1 may
                 // hold stale lines.  Rows are fetched as aligned 32-bit words, four independent loads in flight per thread (a byte
                 // per load made the kernel latency-bound at ~0.4 TB/s); resolutions that are not a multiple of 4 take byte loads.
+                if (tid == 0) prefetch_next();
                 if (p.words) {
                     const int total = X0 * Y0 * WPR, zw0 = (bz >> 2) - HW, lastw = (res >> 2) - 1;
                     uint32_t* s0w = reinterpret_cast<uint32_t*>(s0);
@@ -383,14 +400,14 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
             }
             __syncthreads();
             if (tid == 0) {     // this CTA's contribution to the iteration's counters: one pair of atomics per iteration, below
-                const int old = __ldcg(&p.voteZeros[tile]);
+                const int old = oldvz;
                 if (sh[1] != old) { p.voteZeros[tile] = sh[1]; ctaN += sh[1] - old; }
                 ctaS += sh[0];
                 ++ctaVisits;
             }
             bool fresh = false;
             int nfresh = 0;
-            if (sh[5] >= 0 && tid < 27) {
+            if (tid < 27 && sh[5] >= 0) {
                 // a changed sign at local c moves the votes at c-hh .. c+hl: neighbours whose voxels fall in that range
                 const int dz = tid % 3 - 1, dy = (tid / 3) % 3 - 1, dx = tid / 9 - 1;
                 const bool rx = dx == 0 || (dx < 0 ? sh[2] - hh < 0 : sh[5] + hl >= TX);
@@ -415,9 +432,9 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
                     if (fresh) listNext[basepos + __popc(m & ((1u << tid) - 1u))] = nfresh;
                 }
             }
-            __syncthreads();                     // every thread has read sh_k (= k) and sh[]
-            if (tid == 0) sh_k = knext;
-            __syncthreads();
+            // no barrier here: sh[] is re-initialised by warp 0 itself (program order) and only touched by the other warps
+            // behind the next tile's barriers; the hand-over slot alternates
+            par ^= 1;
         }
         if (tid == 0) {
             if (ctaN) atomicAdd((unsigned long long*)&p.ctrl->slot[cur].dN, (unsigned long long)ctaN);

@@ -143,7 +143,13 @@ def _seed_for(path):
 
 
 def sample_mesh(mesh_file, num_samples, seed=None):
-    """-> [n,3] fp32 CUDA tensor; an unreadable or empty mesh yields [0,3] like the reference (evaluation.py:229-236)."""
+    """-> [n,3] fp32 CUDA tensor; an unreadable or empty mesh yields [0,3] like the reference (evaluation.py:229-236).
+
+    Deviation from the reference (parity unpinned, trimesh is not installed): the reference calls
+    `trimesh.sample.sample_surface_even`, i.e. area-weighted sampling FOLLOWED by an even-spacing rejection that may
+    return fewer than `num_samples` points; this sampler is the area-weighted part only and always returns
+    `num_samples`.  The reference's Chamfer distance is a SUM over the samples, so absolute values are comparable
+    only at equal sample counts (divide by the sample count for a per-sample mean)."""
     dev = _device()
     try:
         verts, faces = mesh_io.read_mesh(mesh_file)

@@ -348,7 +348,7 @@ class TrainStep:
     def step(self, batch):
         """One iteration of the reference's inner loop (points_to_surf_train.py:441-461): zero_grad, forward,
         compute_loss, backward, SGD.  Returns [loss_magnitude, loss_sign] (0-d float64 tensors on the device)."""
-        if self._graph is not None:
+        if self._graph is not None and self._graph_matches(batch):     # a partial last batch takes the eager step
             return self._step_graph(batch)
         logits, losses = self._forward_backward(batch)
         self._reduce_gradients()
@@ -394,9 +394,27 @@ class TrainStep:
         for k, n in bn_before.items():      # the capture pass incremented the host-side counters once: undo
             self.buffers[k].fill_(n)
         self._graph = (g1, g2, static, logits, losses)
+        self._graph_lr = (float(self.lr), float(self.momentum))
         return self
 
+    def _capture_sgd(self):
+        """The SGD kernel takes lr / momentum as launch arguments, i.e. a captured graph bakes them in: re-capture the
+        (one-kernel) update graph whenever the schedule changed them."""
+        g2 = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(g2):
+            self.p.sgd_(self.flat_params, self.flat_grads, self.flat_mom, self.lr, self.momentum, False)
+        g1, _, static, logits, losses = self._graph
+        self._graph = (g1, g2, static, logits, losses)
+        self._graph_lr = (float(self.lr), float(self.momentum))
+
+    def _graph_matches(self, batch):
+        static = self._graph[2]
+        return all(tuple(batch[k].shape) == tuple(static[k].shape) for k in self._BATCH_KEYS)
+
     def _step_graph(self, batch):
+        if (float(self.lr), float(self.momentum)) != self._graph_lr:
+            self._capture_sgd()
         g1, g2, static, logits, losses = self._graph
         for k in self._BATCH_KEYS:
             static[k].copy_(batch[k], non_blocking=True)
