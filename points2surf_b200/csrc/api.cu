@@ -11,7 +11,7 @@ void query_grid(const float* pts, int64_t N, int res, int eps, int32_t* lin_idx,
 void query_points(const int32_t* lin_idx, int64_t Q, int res, float* out, cudaStream_t st);
 void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids, float* patch, float* radius, cudaStream_t st);
 void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int k, double patch_radius, uint64_t seed, int32_t* ids, float* patch, float* radius, int32_t* counts, cudaStream_t st, const int32_t* qidx = nullptr);
-void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr);
+void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr, float* pts_out = nullptr);
 void gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
 void scatter_f32(const float* src, const int32_t* idx, int64_t n, float* dst, cudaStream_t st);
 void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st);
@@ -153,8 +153,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
           else knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
         // the Philox stream is keyed by the query's rank in the whole ordered list -> independent of slabs/batches
         { StageScope t("assemble: subsample+gather", st);
-          subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx);
-          gather_points(pts, b.sub_ids, n * S, b.sub, st); }
+          subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx, b.sub); }
     };
     try {
         for (int64_t q0 = 0; q0 < Q; q0 += batch) {

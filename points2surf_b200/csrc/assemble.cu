@@ -191,21 +191,21 @@ __device__ __forceinline__ float norm_f32(float dx, float dy, float dz) {
 // kth(j+1) <= kth(j) + |q(j+1) - q(j)|): one pass collects every point within that bound (typically 1.1-1.2 k
 // candidates) and an exact sort finishes the job -- no histogram.  The first query of a run, big jumps between
 // queries and overflowing candidate lists fall back to the histogram selection.
-constexpr int kRun = 8;
+constexpr int kRun = 8;        // shortest run; the launcher lengthens it so that the grid is one full wave (see knn_patch)
 
 template <int CAP>
 __global__ void __launch_bounds__(kThreads)
 knn_patch_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int64_t Q, int k,
                  int32_t* __restrict__ ids_out, float* __restrict__ patch_out, float* __restrict__ radius_out,
-                 int* __restrict__ err_flag) {
+                 int* __restrict__ err_flag, int run) {
     constexpr int kCap = CAP;                     // shadows the file-level constant inside this kernel
     __shared__ SelectSmemT<CAP> s;
     __shared__ float red[kThreads / 32];
     __shared__ float s_radius;
     __shared__ double s_kth;          // exact k-th squared distance of the previous query (0 = unknown)
     const int tid = threadIdx.x;
-    const int64_t q_begin = (int64_t)blockIdx.x * kRun;
-    const int64_t q_end = (q_begin + kRun < Q) ? (q_begin + kRun) : Q;
+    const int64_t q_begin = (int64_t)blockIdx.x * run;
+    const int64_t q_end = (q_begin + run < Q) ? (q_begin + run) : Q;
     if (tid == 0) s_kth = 0.0;
     double pqx = 0.0, pqy = 0.0, pqz = 0.0;
     for (int64_t q = q_begin; q < q_end; ++q) {
@@ -584,6 +584,112 @@ subsample_weighted_kernel(const float* __restrict__ pts, int N, const float* __r
     for (unsigned j = tid; n_direct + j < (unsigned)S; j += kThreads) out[q * S + n_direct + j] = s.cand_id[j];
 }
 
+// K3 by rejection: the same successive-sampling law with a quarter of the work when N >= 2 S.
+// Drawing without replacement with probabilities ~ w_i is: propose a point uniformly, accept it with probability w_i
+// (w_i <= 1), skip points that were already taken, repeat until S points are taken.  Proposal j of query q is a fixed
+// function of (seed, q, j) (Philox block j / 2 -> two (index, uniform) pairs), so the accepted set -- the first S distinct
+// accepted proposals in proposal order -- does not depend on how the proposals are spread over threads and rounds.
+// Only ~S / mean(w) * 1.1 ~ 3 400 of the points are touched per query instead of all 10 000 (plus one cheap pass for the
+// maximum distance), and there is no selection or sort.  s_first[i] = position of the first accepted proposal of point i.
+constexpr int kRejPer = 8;        // proposals per thread and round (first round); even
+constexpr int kRejRounds = 256;
+
+__global__ void __launch_bounds__(kThreads)
+subsample_reject_kernel(const float* __restrict__ pts, int N, const float* __restrict__ queries, int64_t qbase,
+                        const int32_t* __restrict__ qidx, int S, uint64_t seed, int32_t* __restrict__ out_ids,
+                        float* __restrict__ out_pts, int* __restrict__ err_flag) {
+    extern __shared__ int s_first[];             // [N]
+    __shared__ float redf[kThreads / 32];
+    __shared__ int redi[kThreads / 32];
+    __shared__ float s_dmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const float qx = queries[q * 3 + 0], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
+    const uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
+    // max_i ||q - p_i|| in float32 like NumPy: sqrt is monotone, so it is the sqrt of the largest float32 squared sum
+    float m2 = 0.f;
+    for (int i = tid; i < N; i += kThreads) {
+        const float dx = __fsub_rn(qx, pts[i * 3 + 0]), dy = __fsub_rn(qy, pts[i * 3 + 1]), dz = __fsub_rn(qz, pts[i * 3 + 2]);
+        m2 = fmaxf(m2, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        s_first[i] = 0x7fffffff;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    if (lane == 0) redf[warp] = m2;
+    __syncthreads();
+    if (tid == 0) {
+        float m = redf[0];
+        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, redf[w]);
+        s_dmax = __fsqrt_rn(m);
+    }
+    __syncthreads();
+    const float dmax = s_dmax;
+    int base = 0;                  // distinct accepted points so far
+    int pos0 = 0;                  // proposals consumed so far
+    int per = kRejPer;             // proposals per thread in this round (even, <= kRejPer)
+    for (int round = 0; round < kRejRounds; ++round) {
+        const int mypos = pos0 + tid * per;
+        int idx[kRejPer];
+        unsigned acc = 0;
+#pragma unroll
+        for (int e2 = 0; e2 < kRejPer / 2; ++e2) {
+            if (2 * e2 < per) {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)((mypos >> 1) + e2), 0x9e3779b1u, r);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = (int)__umulhi(r[2 * h], (uint32_t)N);
+                    // dist_prob (utils.py:200-208) in float32 like NumPy
+                    const float d = norm_f32(__fsub_rn(qx, pts[i * 3 + 0]), __fsub_rn(qy, pts[i * 3 + 1]), __fsub_rn(qz, pts[i * 3 + 2]));
+                    const float w = fminf(fmaxf(__fsub_rn(1.0f, __fmul_rn(1.5f, __fdiv_rn(d, dmax))), 0.05f), 1.0f);
+                    const float u = (float)(r[2 * h + 1] >> 8) * (1.0f / 16777216.0f);     // [0, 1)
+                    idx[2 * e2 + h] = i;
+                    if (u < w) { acc |= 1u << (2 * e2 + h); atomicMin(&s_first[i], mypos + 2 * e2 + h); }
+                }
+            }
+        }
+        __syncthreads();
+        unsigned fresh = 0;
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e)
+            if (((acc >> e) & 1u) && s_first[idx[e]] == mypos + e) fresh |= 1u << e;
+        // exclusive prefix of the fresh counts in thread (= proposal) order
+        const int cnt = __popc(fresh);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) redi[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { const int c = redi[w]; if (w < warp) wbase += c; total += c; }
+        int slot = base + wbase + incl - cnt;
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) {
+            if ((fresh >> e) & 1u) {
+                if (slot < S) {
+                    const int i = idx[e];
+                    out_ids[q * S + slot] = i;
+                    if (out_pts) {
+                        float* o = out_pts + (q * S + slot) * 3;
+                        o[0] = pts[i * 3 + 0]; o[1] = pts[i * 3 + 1]; o[2] = pts[i * 3 + 2];
+                    }
+                }
+                ++slot;
+            }
+        }
+        base += total;
+        if (base >= S) return;
+        pos0 += kThreads * per;
+        // size of the next round from this round's yield (deterministic: block-uniform integers only)
+        const long long need = ((long long)(S - base) * (kThreads * per) * 23 / 20) / (total > 0 ? total : 1) + 1;
+        const long long p2 = (need + 2 * kThreads - 1) / (2 * kThreads);
+        per = (int)(p2 < 1 ? 1 : (p2 > kRejPer / 2 ? kRejPer / 2 : p2)) * 2;
+        __syncthreads();       // redi is reused
+    }
+    if (tid == 0) atomicExch(err_flag, 2);
+}
+
 __global__ void gather_points_kernel(const float* __restrict__ pts, const int32_t* __restrict__ ids, int64_t count, float* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -604,6 +710,8 @@ static int* err_flag_dev() {
     return flag;
 }
 
+void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st);
+
 int assemble_error_check(cudaStream_t st) {  // sync; returns and clears the device error flag
     int h = 0;
     int* f = err_flag_dev();
@@ -619,8 +727,24 @@ void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int
     P2S_CHECK(k >= 1 && k <= kBallMaxK, "k must be in [1, 1536]");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
-    if (k <= 512) P2S_LAUNCH(knn_patch_kernel<kCap>, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
-    else P2S_LAUNCH(knn_patch_kernel<kCapBig>, (unsigned)cdiv(Q, kRun), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev());
+    // Run length: with 8 queries per CTA a batch of 8 192 queries is 1 024 CTAs = 1.4 waves of the 740 co-resident CTAs, i.e.
+    // two waves with the second 38 % full.  Lengthen the runs so that the whole batch is ONE wave (longer runs also amortise
+    // the histogram selection of a run's first query better).
+    static thread_local int slots_small = 0, slots_big = 0;
+    if (!slots_small) {
+        int dev = 0, sms = 0, a = 0, b = 0;
+        P2S_CUDA(cudaGetDevice(&dev));
+        P2S_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, knn_patch_kernel<kCap>, kThreads, 0));
+        P2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, knn_patch_kernel<kCapBig>, kThreads, 0));
+        slots_small = sms * (a > 0 ? a : 1); slots_big = sms * (b > 0 ? b : 1);
+    }
+    const int slots = k <= 512 ? slots_small : slots_big;
+    int run = (int)cdiv(Q, slots);
+    if (run < kRun) run = kRun;
+    if (run > 64) run = 64;
+    if (k <= 512) P2S_LAUNCH(knn_patch_kernel<kCap>, (unsigned)cdiv(Q, run), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev(), run);
+    else P2S_LAUNCH(knn_patch_kernel<kCapBig>, (unsigned)cdiv(Q, run), kThreads, 0, st, pts, (int)N, queries, Q, k, ids, patch, radius, err_flag_dev(), run);
 }
 
 // the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q), like the sub-sampler's
@@ -634,18 +758,31 @@ void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, in
                (float)patch_radius, seed, ids, patch, radius, counts, err_flag_dev());
 }
 
-// the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q)
+// the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q).  pts_out (optional): [Q, S, 3] the selected
+// points themselves (what gather_points would produce from `out`).
 void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S,
-               int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx) {
+               int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx, float* pts_out) {
     P2S_CHECK(N >= S, "sub-sample needs N >= sub_sample_size (reference zero-pads after an in-place shuffle; unsupported)");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
+    bool gathered = false;
     if (mode == P2S_SUBSAMPLE_UNIFORM) {
         int64_t threads = Q * ((S + 3) / 4);
         P2S_LAUNCH(subsample_uniform_kernel, (unsigned)cdiv(threads, 256), 256, 0, st, (int)N, Q, qbase, qidx, S, seed, out);
     } else if (mode == P2S_SUBSAMPLE_WEIGHTED) {
         const size_t cache_bytes = (size_t)N * sizeof(float);
-        if (cache_bytes <= 160 * 1024) {
+        static int no_reject = -1;
+        if (no_reject < 0) { const char* e = getenv("P2S_SUBSAMPLE_CLOCKS"); no_reject = (e && e[0] == '1') ? 1 : 0; }
+        if (cache_bytes <= 160 * 1024 && N >= 2 * (int64_t)S && !no_reject) {
+            // rejection sampling: cheap when at most half of the cloud is drawn (the acceptance rate is >= 0.05 by construction)
+            static thread_local bool attr_set = false;
+            if (!attr_set) {
+                P2S_CUDA(cudaFuncSetAttribute(subsample_reject_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_set = true;
+            }
+            P2S_LAUNCH(subsample_reject_kernel, (unsigned)Q, kThreads, cache_bytes, st, pts, (int)N, queries, qbase, qidx, S, seed, out, pts_out, err_flag_dev());
+            gathered = true;
+        } else if (cache_bytes <= 160 * 1024) {
             static thread_local bool attr_set = false;
             if (!attr_set) {
                 P2S_CUDA(cudaFuncSetAttribute(subsample_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -658,6 +795,7 @@ void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int
     } else {
         throw Error("unknown sub-sample mode");
     }
+    if (pts_out && !gathered) gather_points(pts, out, Q * S, pts_out, st);
 }
 
 __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ dst) {

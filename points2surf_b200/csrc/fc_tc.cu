@@ -34,7 +34,8 @@ struct FcBars {
 
 __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A, int lda, const uint8_t* __restrict__ Wimg,
                                                     const float* __restrict__ bias, float* __restrict__ C, int ldc,
-                                                    int M, int N, int K, int relu, int pack_img) {
+                                                    int M, int N, int K, int relu, int pack_img,
+                                                    const float* __restrict__ in_bias, int in_relu) {
     extern __shared__ __align__(1024) uint8_t smem[];
     FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -71,7 +72,15 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             uint8_t* dst = smem + s * kStageA + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 16u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float x[8] = {v[2 * c].x, v[2 * c].y, v[2 * c].z, v[2 * c].w, v[2 * c + 1].x, v[2 * c + 1].y, v[2 * c + 1].z, v[2 * c + 1].w};
+                float x[8] = {v[2 * c].x, v[2 * c].y, v[2 * c].z, v[2 * c].w, v[2 * c + 1].x, v[2 * c + 1].y, v[2 * c + 1].z, v[2 * c + 1].w};
+                if (in_bias) {          // A = act(A_raw + in_bias[k]): same fp32 operations as a separate bias / ReLU kernel
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(in_bias + kt * kBK + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(in_bias + kt * kBK + c * 8 + 4));
+                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                    if (in_relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+                    }
+                }
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -236,13 +245,13 @@ void fc_tc_init() {
 }
 
 void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bias, float* C, int ldc,
-                  int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img) {
+                  int64_t M, int N, int K, bool relu, cudaStream_t st, int pack_img, const float* in_bias, bool in_relu) {
     if (M <= 0) return;
     const bool padded_ok = !pack_img && N % 4 == 0 && N >= 64 && K % kBK == 0;   // partial last N tile (training GEMMs)
     P2S_CHECK((fc_tc_supported(N, K) || padded_ok) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
     P2S_CHECK(cdiv(M, 128) <= 65535, "too many rows for one launch");
     dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, 128), 1);
-    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img, in_bias, in_relu ? 1 : 0);
 }
 
 // images of a raw fp32 matrix W[N][K] (device pointer)

@@ -86,9 +86,7 @@ struct PassParams {
     int perq_layer;            // index of the mid layer with per-query weights, or -1
     const uint8_t* perq_img;   // [B] x 8192 B (precise: hi | lo, 16384 B)
     const uint8_t* w3_img;     // [8 chunks][32768 B] (precise: [8][hi | lo])  (K-major, LBO 128, SBO 2048)
-    float* out;                // [B,1024] max over the points + b3, optionally ReLU (max(x) + b = max(x + b): the bias is added once per channel)
-    const float* b3;           // [1024] bias of the big layer
-    int out_relu;
+    float* out;                // [B,1024] raw max (bias / ReLU applied by the consumer: the FC kernel's producers add it on load)
     long long* wstats;         // diagnostics: per-role barrier wait cycles (null = off)
 };
 
@@ -532,12 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_pass_kernel(const PassPa
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) {
-                const int ch = (part * C::kChunks + c) * 128 + ch_lane;
-                float o = acc[c] + __ldg(p.b3 + ch);
-                if (p.out_relu) o = fmaxf(o, 0.f);
-                p.out[(size_t)q * 1024 + ch] = o;
-            }
+            for (int c = 0; c < C::kChunks; ++c) p.out[(size_t)q * 1024 + (part * C::kChunks + c) * 128 + ch_lane] = acc[c];
         }
     }
     if (STATS) ws_flush(p.wstats, warp == 8 ? 0 : (warp == 13 ? 1 : (warp < 4 ? 2 : (warp >= 14 ? 4 : (warp >= 9 ? 3 : 5)))), ws, t_begin);
@@ -732,7 +725,7 @@ uint8_t* pack_w3(TcWeights& t, const Layer& L, bool split = false) {   // 8 chun
 }
 
 void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const float* query, const float* R,
-                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, bool out_relu, cudaStream_t st, bool precise) {
+                 int64_t B, int perq_layer, const uint8_t* perq_img, float* out, cudaStream_t st, bool precise) {
     PassParams p{};
     p.seg[0] = s0; p.seg[1] = s1;
     p.query = query; p.R = R;
@@ -745,8 +738,6 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
     p.perq_img = perq_img;
     p.w3_img = precise ? s.w3_img_p : s.w3_img;
     p.out = out;
-    p.b3 = s.b3;
-    p.out_relu = out_relu ? 1 : 0;
     p.wstats = nullptr;
     TcWeights& t = *m.tc;
     static int wstats_on = -1;
@@ -802,15 +793,26 @@ void launch_pass(Model& m, const TcStack& s, const Seg& s0, const Seg& s1, const
 
 Seg make_seg(const float* ptr, int n, int center) { return Seg{ptr, n, n > 0 ? (n + kTile - 1) / kTile : 0, center}; }
 
-void run_fc(const TcFc& f, const float* in, int lda, float* out, int ldc, int64_t Bc, bool relu, bool on_tc, cudaStream_t st) {
+// in_bias (optional, tensor-core kernel only): the layer reads act(in + in_bias) -- the raw max features of a pass get their
+// conv3 bias (and the STN's ReLU) on the way into the first FC layer instead of in separate copy / bias kernels
+void run_fc(const TcFc& f, const float* in, int lda, float* out, int ldc, int64_t Bc, bool relu, bool on_tc, cudaStream_t st,
+            const float* in_bias = nullptr, bool in_relu = false) {
     const Layer& L = *f.L;
-    if (on_tc && f.img) launch_fc_tc(in, lda, f.img, L.b, out, ldc, Bc, L.cout, L.cin, relu, st);
-    else launch_gemm_nt(in, 0, lda, L.W, 0, L.b, out, 0, ldc, (int)Bc, L.cout, L.cin, 1, relu, st);
+    if (on_tc && f.img) launch_fc_tc(in, lda, f.img, L.b, out, ldc, Bc, L.cout, L.cin, relu, st, 0, in_bias, in_relu);
+    else {
+        P2S_CHECK(!in_bias, "input bias needs the tensor-core FC kernel");
+        launch_gemm_nt(in, 0, lda, L.W, 0, L.b, out, 0, ldc, (int)Bc, L.cout, L.cin, 1, relu, st);
+    }
 }
 
-void fc_tail(const TcStnFc& s, bool on_tc, const float* g, int64_t Bc, float* f1, float* f2, float* out, cudaStream_t st) {
-    // g = relu(max + b3) (written by the pass kernel) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
-    run_fc(s.fc1, g, 1024, f1, 512, Bc, true, on_tc, st);
+void fc_tail(const Layer& b3src, const TcStnFc& s, bool on_tc, const float* gmax_raw, int64_t Bc, float* g, float* f1, float* f2, float* out, cudaStream_t st) {
+    // g = relu(max + b3) ; fc1 ; fc2 ; fc3     (model.py:44-64 / 103-122)
+    if (on_tc && s.fc1.img) run_fc(s.fc1, gmax_raw, 1024, f1, 512, Bc, true, true, st, b3src.b, true);
+    else {
+        P2S_CUDA(cudaMemcpyAsync(g, gmax_raw, (size_t)Bc * 1024 * 4, cudaMemcpyDeviceToDevice, st));
+        launch_bias_act(g, b3src.b, Bc, 1024, true, st);
+        run_fc(s.fc1, g, 1024, f1, 512, Bc, true, on_tc, st);
+    }
     run_fc(s.fc2, f1, 512, f2, 256, Bc, true, on_tc, st);
     run_fc(s.fc3, f2, 256, out, s.fc3.L->cout, Bc, false, on_tc, st);
 }
@@ -950,13 +952,13 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
         const float* Rq = nullptr;
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, true, st, precise); }
-            { StageScope ts("net: fc tails", st); fc_tail(t.qstn_fc, fc_tc, gmax, Bc, f1, f2, q4, st); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st, precise); }
+            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st); }
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
-            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, true, st, precise);
-            fc_tail(t.qstn_fc, fc_tc, gmax, Bc, f1, f2, q4, st);
+            launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st, precise);
+            fc_tail(m.global.stn1.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         }
@@ -965,26 +967,33 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
             const Seg sg = br ? make_seg(su, S, 1) : make_seg(pa, P, 0);
             float* fmax = br ? fmax_g : fmax_l;
             // pass B: STN64 -> T
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, true, st, precise); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.stn[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, -1, nullptr, gmax, st, precise); }
             if (fc_tc) {
                 // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
                 StageScope ts("net: fc tails", st);
-                run_fc(t.stn_fc[br].fc1, gmax, 1024, f1, 512, Bc, true, true, st);
+                run_fc(t.stn_fc[br].fc1, gmax, 1024, f1, 512, Bc, true, true, st, f.stn2.c3.b, true);
                 run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
                 launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
             } else {
-                { StageScope ts("net: fc tails", st); fc_tail(t.stn_fc[br], false, gmax, Bc, f1, f2, T, st); }
+                { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], false, gmax, Bc, g, f1, f2, T, st); }
                 // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
                 { StageScope ts("net: fold W1*T", st); P2S_LAUNCH(fold_w1_kernel, (unsigned)Bc, 256, 0, st, f.conv1.W, T, Bc, perq); }
             }
-            (void)Tt; (void)g;
+            (void)Tt;
             // pass C: final stack -> max feature (bias, no ReLU: model.py:203,210-212)
-            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, false, st, precise); }
+            { StageScope ts("net: pass kernels", st); launch_pass(m, t.fin[br], sg, make_seg(nullptr, 0, 0), qu, Rq, Bc, 1, perq, fmax, st, precise); }
+        }
+        // max features = raw max + conv3 bias, no ReLU (model.py:203,210-212): added by the first head FC on load, or by a
+        // separate kernel when the features are exported (debug_aux) or the FCs run on the fp32 kernels
+        const bool fuse_b3 = fc_tc && !m.debug_aux && t.head_fc1[0].img && t.head_fc1[1].img;
+        if (!fuse_b3) {
+            launch_bias_act(fmax_l, m.local.conv3.b, Bc, 1024, false, st);
+            launch_bias_act(fmax_g, m.global.conv3.b, Bc, 1024, false, st);
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
         StageScope ts_head("net: fc tails", st);
-        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, fc_tc, st);
-        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, fc_tc, st);
+        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.local.conv3.b : nullptr, false);
+        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.global.conv3.b : nullptr, false);
         run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, fc_tc, st);
         run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, fc_tc, st);
         launch_gemm_nt(h4, 0, 128, m.fc4.W, 0, m.fc4.b, logits + b0 * 2, 0, 2, (int)Bc, 2, 128, 1, false, st);

@@ -107,7 +107,7 @@ struct PropParams {
     uint8_t* flags[2];
     int* voteZeros;
     Ctrl* ctrl;
-    int res, lo, hi, ntx, nty, ntz, maxIters, words, fast;
+    int res, lo, hi, ntx, nty, ntz, maxIters, words, fast, vec;
     float thr;
 };
 
@@ -180,7 +180,108 @@ __global__ void __launch_bounds__(kPropThreads, 4) propagate_kernel(PropParams p
             const int bx = tx * TX, by = ty * TY, bz = tz * TZ;
             if (tid < 8) sh[tid] = tid < 2 ? 0 : (tid < 5 ? 1 << 20 : -1);
             if (tid == 0) flagCur[tile] = 0;
-            if (SIGMA5 || p.fast) {
+            if (SIGMA5 && p.vec) {
+                // ---- row-vector path (sigma 5, res a multiple of 32: every tile is full and rows are 16-byte aligned).
+                // The packed-word path below is ISSUE-bound (ncu: 2.6 IPC, 8.8 k warp instructions per tile, the volume in L2):
+                // most of its instructions are per-word address arithmetic.  Here one thread owns a whole halo ROW: one address,
+                // two 16-byte loads + two halo words, the z sums of the row straight from registers; the y and x sums are
+                // sliding windows down a column (2 packed adds per output instead of 5 loads + 4 adds), the vote is evaluated
+                // on packed bytes (carry tricks on 16-bit lanes).  ~2 k warp instructions per tile.
+                constexpr int kT1X = 104, kT2X = 72;                                // padded x strides (bank-conflict-free)
+                uint32_t* sraw = reinterpret_cast<uint32_t*>(smem);                // [TX*TY][8]   raw bytes (sign | U0) of the tile
+                uint32_t* t1w = sraw + TX * TY * 8;                                 // [12][kT1X]   sums along z   ([x][y][8])
+                uint32_t* t2w = t1w + 12 * kT1X;                                    // [12][kT2X]   sums along z, y ([x][y][8])
+                const unsigned rw = (unsigned)(res >> 2);
+                if (tid < 144) {
+                    const int x = tid / 12, y = tid - 12 * x;
+                    const int gx = min(max(bx + x - 2, 0), res - 1), gy = min(max(by + y - 2, 0), res - 1);
+                    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(in) + (unsigned)(gx * res + gy) * rw + (unsigned)(bz >> 2);
+                    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(rowp));
+                    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(rowp) + 1);
+                    const bool lft = bz > 0, rgt = bz + TZ < res;
+                    uint32_t hl_w = lft ? __ldcg(rowp - 1) : 0u, hr_w = rgt ? __ldcg(rowp + 8) : 0u;
+                    if (tid == 0) prefetch_next();
+                    if (!lft) hl_w = (a.x & 0xffu) * 0x01010101u;                   // 'nearest': first voxel of the row
+                    if (!rgt) hr_w = (b.w >> 24) * 0x01010101u;                     // last voxel of the row
+                    if ((unsigned)(x - 2) < (unsigned)TX && (unsigned)(y - 2) < (unsigned)TY) {
+                        uint4* d = reinterpret_cast<uint4*>(sraw + ((x - 2) * TY + (y - 2)) * 8);
+                        d[0] = a; d[1] = b;
+                    }
+                    uint32_t c[10] = {hl_w, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, hr_w};
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) c[i] = ((c[i] & 0x03030303u) + 0x01010101u) & 0x03030303u;     // 2-bit sign -> sign + 1
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = __funnelshift_r(c[j], c[j + 1], 16) + __funnelshift_r(c[j], c[j + 1], 24) + c[j + 1] +
+                               __funnelshift_r(c[j + 1], c[j + 2], 8) + __funnelshift_r(c[j + 1], c[j + 2], 16);
+                    uint4* d = reinterpret_cast<uint4*>(t1w + x * kT1X + y * 8);
+                    d[0] = make_uint4(o[0], o[1], o[2], o[3]); d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                __syncthreads();
+                if (tid < 96) {                                                     // sums along y: thread = (x, word), window slides down y
+                    const int j = tid & 7, x = tid >> 3;
+                    const uint32_t* r = t1w + x * kT1X + j;
+                    uint32_t v[12];
+#pragma unroll
+                    for (int y = 0; y < 12; ++y) v[y] = r[y * 8];
+                    uint32_t acc = v[0] + v[1] + v[2] + v[3] + v[4];
+                    uint32_t* w = t2w + x * kT2X + j;
+                    w[0] = acc;
+#pragma unroll
+                    for (int y = 1; y < 8; ++y) { acc = acc - v[y - 1] + v[y + 4]; w[y * 8] = acc; }   // bytes never borrow: v[y-1] is part of acc
+                }
+                __syncthreads();
+                {   // sums along x, vote, apply: thread = (x pair, y, word)
+                    const int j = tid & 7, y = (tid >> 3) & 7, x0 = (tid >> 6) * 2;
+                    const uint32_t* r = t2w + x0 * kT2X + y * 8 + j;
+                    const uint32_t v0 = r[0], v1 = r[kT2X], v2 = r[2 * kT2X], v3 = r[3 * kT2X], v4 = r[4 * kT2X], v5 = r[5 * kT2X];
+                    const uint32_t sum0 = v0 + v1 + v2 + v3 + v4;
+                    const uint32_t sumv[2] = {sum0, sum0 - v0 + v5};
+                    // vote per byte: n = sum - 125; +1 iff n >= T, -1 iff n <= -T with T = max(ceil(thr), 1) (|n| < thr or n == 0 -> 0)
+                    const int T = min(max(ithr, 1), 126);
+                    const uint32_t cpos = (uint32_t)(0x100 - (125 + T)) * 0x00010001u, cneg = (uint32_t)(0x100 + 125 - T) * 0x00010001u;
+                    int dS = 0, nz = 0, mnx = 1 << 20, mxx = -1, mny = 1 << 20, mxy = -1, mnz = 1 << 20, mxz = -1;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int x = x0 + u;
+                        const uint32_t sum = sumv[u];
+                        const uint32_t e = sum & 0x00ff00ffu, o = (sum >> 8) & 0x00ff00ffu;
+                        const uint32_t pe = ((e + cpos) >> 8) & 0x00010001u, po = ((o + cpos) >> 8) & 0x00010001u;
+                        const uint32_t ne = ((cneg - e) >> 8) & 0x00010001u, no = ((cneg - o) >> 8) & 0x00010001u;
+                        nz += 4 - __popc(pe | ne) - __popc(po | no);
+                        const uint32_t ve = pe | (ne * 3u), vo = po | (no * 3u);
+                        const uint32_t cand = ve | (vo << 8) | 0x04040404u;         // the four votes as sign bytes with the U0 flag
+                        const uint32_t raw = sraw[(x * TY + y) * 8 + j];
+                        const uint32_t um = ((raw >> 2) & 0x01010101u) * 0xffu;     // 0xff in the bytes that were unknown at the start
+                        const uint32_t neww = (raw & ~um) | (cand & um);
+                        reinterpret_cast<uint32_t*>(out)[(unsigned)((bx + x) * res + by + y) * rw + (unsigned)((bz >> 2) + j)] = neww;
+                        const uint32_t diff = neww ^ raw;
+                        if (diff) {                                               // rare: signs change only along the front
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if ((diff >> (8 * q)) & 0xffu) {
+                                    dS += (int)(((neww >> (8 * q)) & 3u) == 0u) - (int)(((raw >> (8 * q)) & 3u) == 0u);
+                                    const int z = 4 * j + q;
+                                    mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y); mnz = min(mnz, z); mxz = max(mxz, z);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { dS += __shfl_xor_sync(0xffffffffu, dS, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
+                    if (__any_sync(0xffffffffu, mxx >= 0)) {                       // one set of shared atomics per warp, not per voxel
+                        mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+                        mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+                        mnz = __reduce_min_sync(0xffffffffu, mnz); mxz = __reduce_max_sync(0xffffffffu, mxz);
+                        if ((tid & 31) == 0) {
+                            atomicMin(&sh[2], mnx); atomicMax(&sh[5], mxx); atomicMin(&sh[3], mny); atomicMax(&sh[6], mxy);
+                            atomicMin(&sh[4], mnz); atomicMax(&sh[7], mxz);
+                        }
+                    }
+                    if ((tid & 31) == 0) { if (dS) atomicAdd(&sh[0], dS); if (nz) atomicAdd(&sh[1], nz); }
+                }
+            } else if (SIGMA5 || p.fast) {
                 // ---- fast path (word-aligned rows, sigma <= 5): four voxels per 32-bit word everywhere.  Signs are held BIASED
                 // (sign + 1 in {0,1,2}) so that plain integer adds on packed words are exact box sums: no byte ever exceeds
                 // 2 * 5^3 = 250, so nothing carries into its neighbour.  (The byte-at-a-time version spent ~24 k warp
@@ -532,6 +633,11 @@ void sdf_to_volume(const int32_t* lin_idx, const float* sdf, int64_t Q, int res,
     (void)Z0;
     pp.words = (res % 4 == 0) ? 1 : 0;       // aligned 32-bit row loads need word-aligned rows
     pp.fast = (pp.words && sigma <= 5) ? 1 : 0;   // packed biased-byte sums need 2 * sigma^3 <= 255
+    {
+        static int novec = -1;
+        if (novec < 0) { const char* e = getenv("P2S_VOL_NOVEC"); novec = (e && e[0] == '1') ? 1 : 0; }
+        pp.vec = (sigma == 5 && res % 32 == 0 && !novec) ? 1 : 0;   // row-vector path: full tiles, 16-byte aligned rows
+    }
     const size_t smem_generic = (size_t)((X0 * Y0 * ZS + 15) & ~15) + (size_t)((X0 * Y0 * TZ + 15) & ~15) + (size_t)X0 * TY * TZ * 2;
     const size_t smem_fast = 4 * ((size_t)X0 * Y0 * (ZS / 4) + (size_t)TX * TY * 8 + (size_t)X0 * Y0 * 8 + (size_t)X0 * TY * 8);
     const size_t smem = pp.fast ? smem_fast : smem_generic;

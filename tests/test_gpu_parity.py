@@ -195,7 +195,9 @@ def test_sign_propagation_golden(name):
 
 
 # res % 4 == 0 and sigma <= 5 take the word-wide kernels, the rest the scalar ones
-@pytest.mark.parametrize('res,sigma,thr', [(24, 5, 13), (33, 4, 9), (48, 5, 26), (20, 2, 3), (36, 4, 9), (44, 7, 40), (64, 1, 1), (52, 3, 5)])
+# res % 32 == 0 with sigma 5 takes the row-vector path (full tiles, 16-byte row loads, packed-byte votes)
+@pytest.mark.parametrize('res,sigma,thr', [(24, 5, 13), (33, 4, 9), (48, 5, 26), (20, 2, 3), (36, 4, 9), (44, 7, 40), (64, 1, 1), (52, 3, 5),
+                                           (32, 5, 13), (64, 5, 13), (64, 5, 0.5), (96, 5, 13), (128, 5, 13), (64, 5, 200)])
 def test_sign_propagation_vs_oracle(res, sigma, thr):
     cloud = synth.make_cloud('torus', 4000, seed=9)
     qpts = orc.query_grid(cloud, res, 3)
@@ -207,6 +209,25 @@ def test_sign_propagation_vs_oracle(res, sigma, thr):
     lin = ((idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2]).astype(np.int32)
     vol, _ = ops.sdf_to_volume(cu(lin), cu(d), res, sigma, float(thr))
     assert np.array_equal(vol.cpu().numpy().astype(np.float64), ref)
+
+
+@pytest.mark.parametrize('res,noise,thr', [(32, 0.0, 13), (64, 0.0, 13), (64, 0.02, 13), (96, 0.01, 13), (128, 0.005, 13), (64, 0.0, 0.5), (64, 0.02, 20)])
+def test_sign_propagation_row_vector_path_vs_oracle(res, noise, thr):
+    # a real signed-distance band (sphere + noise): the fronts travel through the whole volume, volumes AND iteration counts
+    # must equal the reference algorithm's
+    cloud = synth.make_cloud('sphere', 6000, seed=4)
+    qpts = orc.query_grid(cloud, res, 3)
+    rng = np.random.RandomState(res + int(noise * 1000))
+    r0 = float(np.linalg.norm(cloud, axis=1).mean())
+    d = (np.linalg.norm(qpts, axis=1) - r0 + noise * rng.standard_normal(len(qpts))).astype(np.float32)
+    vol_ref = orc.add_samples_to_volume(np.zeros((res,) * 3), qpts, d)
+    vol_ref, it_ref = orc.propagate_sign(vol_ref, 5, thr)
+    assert it_ref >= 3
+    idx = orc.model_space_to_volume_space(qpts, res)
+    lin = ((idx[:, 0] * res + idx[:, 1]) * res + idx[:, 2]).astype(np.int32)
+    vol, iters = ops.sdf_to_volume(cu(lin), cu(d), res, 5, float(thr))
+    assert iters == it_ref
+    assert np.array_equal(vol.cpu().numpy().astype(np.float64), np.clip(vol_ref, -1.0, 1.0))
 
 
 def test_all_zero_band_is_reported():
