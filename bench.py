@@ -432,14 +432,18 @@ def run_b200(args):
             vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
             mv, mf = ops.marching_cubes(vol, 0.0)
         barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
-        e1.record()
-        mv, mf = ops.marching_cubes(vol, 0.0)
-        e2.record()
-        torch.cuda.synchronize()
-        t_vol, t_mc = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        # five timed repetitions, median of each stage (single 2-3 ms calls next to the clock sampler are noisy)
+        tv, tm = [], []
+        for _ in range(5):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            vol, iters = ops.sdf_to_volume(lin, sdf, res, 5, 13.0)
+            e1.record()
+            mv, mf = ops.marching_cubes(vol, 0.0)
+            e2.record()
+            torch.cuda.synchronize()
+            tv.append(e0.elapsed_time(e1)); tm.append(e1.elapsed_time(e2))
+        t_vol, t_mc = sorted(tv)[2], sorted(tm)[2]
         # final mesh gather to rank 0 (NCCL over NVLink; the only data-path communication of the sharded run)
         t_gather, gathered = 0.0, 1
         if world > 1:
@@ -459,7 +463,7 @@ def run_b200(args):
                       'sign_propagation_frac_of_hbm_peak': vox * 2.0 * (max(iters, 0) + 1) / (t_vol * 1e-3) / 1e9 / float(peaks_hbm),
                       'marching_cubes_ms': t_mc, 'verts': int(mv.shape[0]), 'faces': int(mf.shape[0]),
                       'marching_cubes_GBps': (vox * 4.0 * 2 + vox * 20.0 + mv.shape[0] * 12.0 + mf.shape[0] * 12.0) / (t_mc * 1e-3) / 1e9,
-                      'bytes_model': 'sign propagation: SURVEY 8d algorithmic bytes = res^3 * 2 B per vote evaluation (iterations + 1; the whole scatter/init/propagate/finalize call is timed); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
+                      'bytes_model': 'sign propagation: SURVEY 8d algorithmic bytes = res^3 * 2 B per vote evaluation (iterations + 1; the whole scatter/init/propagate/finalize call is timed, median of 5); MC: res^3 * (2 x 4 B volume reads + 20 B scan scratch) + mesh bytes',
                       'mesh_gather_ms': float(tt[1].item()), 'meshes_on_rank0': gathered,
                       'shapes_per_s_incl_mesh': world * 1e3 / (dev_ms / args.steps + float(tt[0].item()) + float(tt[1].item()))}
     sampler.stop_flag = True

@@ -32,17 +32,23 @@ struct FcBars {
     uint32_t tmem_base;
 };
 
+// A operand: fp32 rows (converted by the producer warps, `A`) or a pre-packed operand image `Aimg`
+// ([M/128][K/32][hi | lo][128 x 32 fp16], the W layout): then the producers have nothing to do and both operands of a k-step
+// arrive by bulk copy.  ncu showed the fp32 mode L1TEX-bound (61-77 % l1tex throughput, 17-19 % tensor-active): every A
+// element was loaded and split once per N tile (4x for the 1024->512 layers, 32x for the folded 256->4096 layer) through
+// row-per-thread loads.  pack_img == 3 writes C as the NEXT layer's operand image (k-steps out_kt_off.. of out_kt_total).
 __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A, int lda, const uint8_t* __restrict__ Wimg,
                                                     const float* __restrict__ bias, float* __restrict__ C, int ldc,
                                                     int M, int N, int K, int relu, int pack_img,
-                                                    const float* __restrict__ in_bias, int in_relu) {
+                                                    const float* __restrict__ in_bias, int in_relu,
+                                                    const uint8_t* __restrict__ Aimg, int out_kt_total, int out_kt_off) {
     extern __shared__ __align__(1024) uint8_t smem[];
     FcBars* bars = reinterpret_cast<FcBars*>(smem + kStages * (kStageA + kStageB));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.y * 128, nt = blockIdx.x;   // N tiles of one row block are adjacent: A is re-read from L2
     const int nk = K / kBK;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 129); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], Aimg ? 1 : 129); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->d_full, 1);
         fence_mbar_init();
     }
@@ -60,9 +66,12 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
         // stage of loads per thread the producers were latency-bound: ~800 cycles of L2 latency per 384 cycles of MMA)
         float4 v[8], nv[8];
         const bool row_ok = row < M;
+        const int nk_prod = Aimg ? 0 : nk;           // operand image: nothing to produce
+        if (!Aimg) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = row_ok ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kt = 0; kt < nk; ++kt) {
+            for (int j = 0; j < 8; ++j) v[j] = row_ok ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int kt = 0; kt < nk_prod; ++kt) {
             const int s = kt % kStages;
             const uint32_t use = (uint32_t)(kt / kStages);
             const bool more = row_ok && (kt + 1 < nk);
@@ -109,7 +118,28 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
             uint32_t r[32];
             tmem_ld_x32(tmem + lane_base + n0, r);
             tmem_ld_wait();
-            if (row < M && pack_img) {
+            if (pack_img == 3) {
+                // C as the next layer's A operand image: this 32-column chunk is exactly one k-step of that layer
+                uint8_t* blk = reinterpret_cast<uint8_t*>(C) + ((size_t)blockIdx.y * out_kt_total + out_kt_off + nt * 4 + (n0 >> 5)) * (size_t)kStageA +
+                               (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 16u;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x0 = __uint_as_float(r[g * 8 + 2 * e]) + b[n0 + g * 8 + 2 * e], x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) + b[n0 + g * 8 + 2 * e + 1];
+                        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        if (row >= M) { x0 = 0.f; x1 = 0.f; }
+                        __half2 h = __floats2half2_rn(x0, x1);
+                        float2 hf = __half22float2(h);
+                        __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                        hi[e] = *reinterpret_cast<uint32_t*>(&h);
+                        lo[e] = *reinterpret_cast<uint32_t*>(&l);
+                    }
+                    *reinterpret_cast<uint4*>(blk + g * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(blk + kHalf + g * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            } else if (row < M && pack_img) {
                 // C is a per-row fp16 operand image of a [64][64] matrix (row-major index = column of this GEMM):
                 // K-major, LBO 128, SBO 1024 -- the per-query B operand of the pass kernel
                 // pack_img == 2: split precision, 16384 B per row: hi image | lo image
@@ -150,11 +180,13 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
         const uint64_t dsc_a = make_smem_desc(smem_u32(smem), 128, 512);
         const uint64_t dsc_b = make_smem_desc(smem_u32(smem + kStages * kStageA), 128, 512);
         const uint8_t* wsrc = Wimg + (size_t)nt * nk * kStageB;
-        // prefetch the first stages of W
+        const uint8_t* asrc = Aimg ? Aimg + (size_t)blockIdx.y * nk * kStageA : nullptr;
+        // prefetch the first stages of W (and of A in image mode)
         for (int kt = 0; kt < nk && kt < kStages; ++kt) {
             if (elect_one()) {
-                mbar_arrive_expect_tx(&bars->full[kt], kStageB);
+                mbar_arrive_expect_tx(&bars->full[kt], kStageB + (asrc ? kStageA : 0u));
                 bulk_g2s(smem + kStages * kStageA + kt * kStageB, wsrc + (size_t)kt * kStageB, kStageB, &bars->full[kt]);
+                if (asrc) bulk_g2s(smem + kt * kStageA, asrc + (size_t)kt * kStageA, kStageA, &bars->full[kt]);
             }
             __syncwarp();
         }
@@ -184,8 +216,9 @@ __global__ void __launch_bounds__(160) fc_tc_kernel(const float* __restrict__ A,
                     const int sp = kp % kStages;
                     mbar_wait_bounded(&bars->empty[sp], (uint32_t)(kp / kStages) & 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&bars->full[sp], kStageB);
+                        mbar_arrive_expect_tx(&bars->full[sp], kStageB + (asrc ? kStageA : 0u));
                         bulk_g2s(smem + kStages * kStageA + sp * kStageB, wsrc + (size_t)kn * kStageB, kStageB, &bars->full[sp]);
+                        if (asrc) bulk_g2s(smem + sp * kStageA, asrc + (size_t)kn * kStageA, kStageA, &bars->full[sp]);
                     }
                     __syncwarp();
                 }
@@ -208,6 +241,32 @@ __global__ void pack_fc_kernel(const float* __restrict__ W, int N, int K, uint8_
     const __half h = __float2half_rn(w);
     *reinterpret_cast<__half*>(img + off) = h;
     *reinterpret_cast<__half*>(img + off + kHalf) = __float2half_rn(w - __half2float(h));
+}
+
+// fp32 activations A[M][K] (+ optional bias / ReLU) -> A operand images [ceil(M/128)][K/32][hi | lo][128 x 32 fp16, K-major,
+// LBO 128, SBO 512]; rows >= M are zero.  One CTA per (row tile, k-step): 8 lanes read one row's 128 bytes (coalesced).
+__global__ void __launch_bounds__(256) pack_a_kernel(const float* __restrict__ A, int lda, int M, int K, const float* __restrict__ in_bias,
+                                                     int in_relu, uint8_t* __restrict__ img) {
+    const int kt = blockIdx.x, mt = blockIdx.y, c = threadIdx.x & 7;
+    uint8_t* blk = img + ((size_t)mt * (K / kBK) + kt) * (size_t)kStageA;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_bias) b4 = __ldg(reinterpret_cast<const float4*>(in_bias + kt * kBK + c * 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (threadIdx.x >> 3) + 32 * i, row = mt * 128 + r;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M) {
+            x = *reinterpret_cast<const float4*>(A + (int64_t)row * lda + kt * kBK + c * 4);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        }
+        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), l1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+        const uint32_t off = (uint32_t)(r >> 3) * 512u + (uint32_t)(c >> 1) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 1) * 8u;
+        *reinterpret_cast<uint2*>(blk + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(blk + kHalf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
 }
 
 // same image for N rows padded with zeros to Npad (multiple of 128)
@@ -251,7 +310,30 @@ void launch_fc_tc(const float* A, int lda, const uint8_t* Wimg, const float* bia
     P2S_CHECK((fc_tc_supported(N, K) || padded_ok) && lda % 4 == 0 && (pack_img ? N == 4096 : ldc % 4 == 0), "bad FC shape for the tensor-core kernel");
     P2S_CHECK(cdiv(M, 128) <= 65535, "too many rows for one launch");
     dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, 128), 1);
-    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img, in_bias, in_relu ? 1 : 0);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, A, lda, Wimg, bias, C, ldc, (int)M, N, K, relu ? 1 : 0, pack_img, in_bias, in_relu ? 1 : 0,
+               (const uint8_t*)nullptr, 0, 0);
+}
+
+size_t fc_tc_a_image_bytes(int64_t M, int K) { return (size_t)cdiv(M, 128) * (size_t)(K / kBK) * kStageA; }
+
+void launch_pack_a(const float* A, int lda, int64_t M, int K, const float* in_bias, bool in_relu, uint8_t* img, cudaStream_t st) {
+    if (M <= 0) return;
+    P2S_CHECK(K % kBK == 0 && lda % 4 == 0 && cdiv(M, 128) <= 65535, "bad shape for the A operand image");
+    dim3 grid((unsigned)(K / kBK), (unsigned)cdiv(M, 128), 1);
+    P2S_LAUNCH(pack_a_kernel, grid, 256, 0, st, A, lda, (int)M, K, in_bias, in_relu ? 1 : 0, img);
+}
+
+// A given as an operand image (launch_pack_a or a previous layer's out_mode 3).  out_mode: 0 fp32 row-major C (ldc), 1 / 2 the
+// per-query operand image of the pass kernel (N == 4096), 3 the next layer's A image (k-steps out_kt_off.. of out_kt_total).
+void launch_fc_tc_img(const uint8_t* Aimg, const uint8_t* Wimg, const float* bias, void* C, int ldc, int64_t M, int N, int K,
+                      bool relu, cudaStream_t st, int out_mode, int out_kt_total, int out_kt_off) {
+    if (M <= 0) return;
+    P2S_CHECK(fc_tc_supported(N, K) && Aimg && (out_mode == 0 ? ldc % 4 == 0 : (out_mode == 3 ? out_kt_off + N / 32 <= out_kt_total : N == 4096)),
+              "bad FC shape for the tensor-core kernel (operand-image mode)");
+    P2S_CHECK(cdiv(M, 128) <= 65535, "too many rows for one launch");
+    dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, 128), 1);
+    P2S_LAUNCH(fc_tc_kernel, grid, 160, kFcSmem, st, (const float*)nullptr, 0, Wimg, bias, reinterpret_cast<float*>(C), ldc, (int)M, N, K, relu ? 1 : 0,
+               out_mode, (const float*)nullptr, 0, Aimg, out_kt_total, out_kt_off);
 }
 
 // images of a raw fp32 matrix W[N][K] (device pointer)

@@ -934,7 +934,8 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
     const int P = m.cfg.points_per_patch, S = m.cfg.sub_sample_size;
     const int64_t Bc_max = 8192;
     // workspace (floats per query)
-    const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 4096 /* 16 KB perq image (hi | lo) */ + 16;
+    const size_t per_q = 1024 * 4 + 512 + 256 + 4 + 9 + 4096 * 2 + 1024 + 256 + 128 + 4096 /* 16 KB perq image (hi | lo) */ + 16 +
+                         1024 + 512 + 256 /* A operand images of the FC tails (4 B per element: hi + lo fp16) */;
     float* base = m.ws_net.as<float>(per_q * (size_t)Bc_max + 1024);
     float* pcur = base;
     auto take = [&](size_t n) { float* r = pcur; pcur += (n * (size_t)Bc_max + 63) / 64 * 64; return r; };
@@ -942,7 +943,19 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
     float* q4 = take(4); float* R = take(9); float* T = take(4096); float* Tt = take(4096);
     float* fmax_l = take(1024); float* fmax_g = take(1024); float* cat = take(1024); float* h3 = take(256); float* h4 = take(128);
     uint8_t* perq = reinterpret_cast<uint8_t*>(take(4096));
+    // A operand images (hi | lo fp16, 4 B per element; Bc_max is a multiple of 128): K = 1024, 512, 256
+    uint8_t* imgA = reinterpret_cast<uint8_t*>(take(1024)); uint8_t* imgB = reinterpret_cast<uint8_t*>(take(512)); uint8_t* imgC = reinterpret_cast<uint8_t*>(take(256));
     const bool fc_tc = t.fc_on_tc || precise;   // the precise path needs the split-precision FC kernel's image output
+    // FC tails as a chain of operand images: the raw max features are packed once (bias + ReLU on the way), every layer reads
+    // its A operand by bulk copy and writes its output as the next layer's image -- no per-N-tile re-conversion of A
+    auto img_ok = [](const TcStnFc& f) { return f.fc1.img && f.fc2.img; };
+    // gmax_raw [Bc,1024] -> relu(+b3) -> fc1 -> fc2; f2 as fp32 rows (out_f2) or as an image in imgC
+    auto stn_tail_img = [&](const Layer& c3, const TcStnFc& f, const float* gmax_raw, int64_t Bc, float* out_f2) {
+        launch_pack_a(gmax_raw, 1024, Bc, 1024, c3.b, true, imgA, st);
+        launch_fc_tc_img(imgA, f.fc1.img, f.fc1.L->b, imgB, 0, Bc, 512, 1024, true, st, 3, 16, 0);
+        if (out_f2) launch_fc_tc_img(imgB, f.fc2.img, f.fc2.L->b, out_f2, 256, Bc, 256, 512, true, st, 0);
+        else launch_fc_tc_img(imgB, f.fc2.img, f.fc2.L->b, imgC, 0, Bc, 256, 512, true, st, 3, 8, 0);
+    };
 
     for (int64_t b0 = 0; b0 < B; b0 += Bc_max) {
         const int64_t Bc = (B - b0 < Bc_max) ? (B - b0) : Bc_max;
@@ -953,12 +966,19 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
         if (m.shared_qstn) {
             // pass A over cat(patch, sub - q)   (model.py:303,325-327)
             { StageScope ts("net: pass kernels", st); launch_pass(m, t.qstn, make_seg(pa, P, 0), make_seg(su, S, 1), qu, nullptr, Bc, -1, nullptr, gmax, st, precise); }
-            { StageScope ts("net: fc tails", st); fc_tail(m.point_stn.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st); }
+            { StageScope ts("net: fc tails", st);
+              if (fc_tc && img_ok(t.qstn_fc)) {
+                  stn_tail_img(m.point_stn.c3, t.qstn_fc, gmax, Bc, f2);
+                  run_fc(t.qstn_fc.fc3, f2, 256, q4, 4, Bc, false, false, st);
+              } else fc_tail(m.point_stn.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st); }
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         } else if (m.global.has_qstn) {
             launch_pass(m, t.qstn, make_seg(su, S, 1), make_seg(nullptr, 0, 0), qu, nullptr, Bc, -1, nullptr, gmax, st, precise);
-            fc_tail(m.global.stn1.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st);
+            if (fc_tc && img_ok(t.qstn_fc)) {
+                stn_tail_img(m.global.stn1.c3, t.qstn_fc, gmax, Bc, f2);
+                run_fc(t.qstn_fc.fc3, f2, 256, q4, 4, Bc, false, false, st);
+            } else fc_tail(m.global.stn1.c3, t.qstn_fc, fc_tc, gmax, Bc, g, f1, f2, q4, st);
             launch_quat_to_rot(q4, R, Bc, st);
             Rq = R;
         }
@@ -971,9 +991,14 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
             if (fc_tc) {
                 // fc1, fc2, then the folded last layer writes the per-query fp16 operand images of conv1*(T+I) directly
                 StageScope ts("net: fc tails", st);
-                run_fc(t.stn_fc[br].fc1, gmax, 1024, f1, 512, Bc, true, true, st, f.stn2.c3.b, true);
-                run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
-                launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
+                if (img_ok(t.stn_fc[br])) {
+                    stn_tail_img(f.stn2.c3, t.stn_fc[br], gmax, Bc, nullptr);
+                    launch_fc_tc_img(imgC, t.fold_img[br], t.fold_bias[br], perq, 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
+                } else {
+                    run_fc(t.stn_fc[br].fc1, gmax, 1024, f1, 512, Bc, true, true, st, f.stn2.c3.b, true);
+                    run_fc(t.stn_fc[br].fc2, f1, 512, f2, 256, Bc, true, true, st);
+                    launch_fc_tc(f2, 256, t.fold_img[br], t.fold_bias[br], reinterpret_cast<float*>(perq), 0, Bc, 4096, 256, false, st, precise ? 2 : 1);
+                }
             } else {
                 { StageScope ts("net: fc tails", st); fc_tail(f.stn2.c3, t.stn_fc[br], false, gmax, Bc, g, f1, f2, T, st); }
                 // W1' = conv1.W * (T + I) -> per-query fp16 operand images (one fused kernel)
@@ -992,10 +1017,21 @@ static void forward_tc_core(Model& m, const float* patch, const float* sub, cons
         }
         debug_aux_copy(m, b0, Bc, Rq, fmax_l, fmax_g, st);
         StageScope ts_head("net: fc tails", st);
-        run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.local.conv3.b : nullptr, false);
-        run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.global.conv3.b : nullptr, false);
-        run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, fc_tc, st);
-        run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, fc_tc, st);
+        if (fuse_b3 && t.head_fc2.img && t.head_fc3.img) {
+            // cat(local, global) (model.py:335,343,346) is the K = 1024 operand image of fc2: k-steps 0-15 local, 16-31 global
+            uint8_t* imgCat = reinterpret_cast<uint8_t*>(cat);            // [Bc,1024] x 4 B: same footprint as the fp32 rows
+            launch_pack_a(fmax_l, 1024, Bc, 1024, m.local.conv3.b, false, imgA, st);
+            launch_fc_tc_img(imgA, t.head_fc1[0].img, m.fc1_local.b, imgCat, 0, Bc, 512, 1024, true, st, 3, 32, 0);
+            launch_pack_a(fmax_g, 1024, Bc, 1024, m.global.conv3.b, false, imgA, st);
+            launch_fc_tc_img(imgA, t.head_fc1[1].img, m.fc1_global.b, imgCat, 0, Bc, 512, 1024, true, st, 3, 32, 16);
+            launch_fc_tc_img(imgCat, t.head_fc2.img, m.fc2.b, imgC, 0, Bc, 256, 1024, true, st, 3, 8, 0);
+            launch_fc_tc_img(imgC, t.head_fc3.img, m.fc3.b, h4, 128, Bc, 128, 256, true, st, 0);
+        } else {
+            run_fc(t.head_fc1[0], fmax_l, 1024, cat, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.local.conv3.b : nullptr, false);
+            run_fc(t.head_fc1[1], fmax_g, 1024, cat + 512, 1024, Bc, true, fc_tc, st, fuse_b3 ? m.global.conv3.b : nullptr, false);
+            run_fc(t.head_fc2, cat, 1024, h3, 256, Bc, true, fc_tc, st);
+            run_fc(t.head_fc3, h3, 256, h4, 128, Bc, true, fc_tc, st);
+        }
         launch_gemm_nt(h4, 0, 128, m.fc4.W, 0, m.fc4.b, logits + b0 * 2, 0, 2, (int)Bc, 2, 128, 1, false, st);
     }
 }
