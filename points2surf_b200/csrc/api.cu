@@ -11,7 +11,10 @@ void query_grid(const float* pts, int64_t N, int res, int eps, int32_t* lin_idx,
 void query_points(const int32_t* lin_idx, int64_t Q, int res, float* out, cudaStream_t st);
 void knn_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int k, int32_t* ids, float* patch, float* radius, cudaStream_t st);
 void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int k, double patch_radius, uint64_t seed, int32_t* ids, float* patch, float* radius, int32_t* counts, cudaStream_t st, const int32_t* qidx = nullptr);
-void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr, float* pts_out = nullptr);
+struct CloudIndex;
+bool cloud_index_usable(int64_t N, int S, int mode);
+const CloudIndex* cloud_index_build(const float* pts, int64_t N, cudaStream_t st);
+void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S, int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx = nullptr, float* pts_out = nullptr, const CloudIndex* cidx = nullptr);
 void gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
 void scatter_f32(const float* src, const int32_t* idx, int64_t n, float* dst, cudaStream_t st);
 void gather_points(const float* pts, const int32_t* ids, int64_t count, float* out, cudaStream_t st);
@@ -146,6 +149,8 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
         P2S_CUDA(cudaMemsetAsync(gcount, 0, sizeof(int), st));
         m.guard_list = glist; m.guard_list_count = gcount; m.guard_list_cap = Q;
     }
+    // cell index of the cloud for the weighted sub-sampler: once per shape
+    const CloudIndex* cidx = cloud_index_usable(N, S, rc.subsample_mode) ? cloud_index_build(pts, N, st) : nullptr;
     auto assemble = [&](const int32_t* lin, int64_t n, int64_t qbase, const int32_t* qidx) {
         query_points(lin, n, rc.res, b.qpts, st);
         { StageScope t("assemble: knn_patch", st);
@@ -153,7 +158,7 @@ static void reconstruct(Model& m, const p2s_recon_config& rc, const float* pts, 
           else knn_patch(pts, N, b.qpts, n, P, nullptr, b.patch, b.radius, st); }
         // the Philox stream is keyed by the query's rank in the whole ordered list -> independent of slabs/batches
         { StageScope t("assemble: subsample+gather", st);
-          subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx, b.sub); }
+          subsample(pts, N, b.qpts, n, qbase, S, rc.subsample_mode, rc.seed, b.sub_ids, st, qidx, b.sub, cidx); }
     };
     try {
         for (int64_t q0 = 0; q0 < Q; q0 += batch) {

@@ -8,8 +8,18 @@
 // One CTA per query; the cloud (N*12 B, L1/L2-resident) is streamed twice per selection:
 // a histogram pass over the top bits of the (monotone) key, then a collect pass.  All byte/compare work.
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace p2s {
+
+// per-cloud cell index of the weighted sub-sampler (device pointers; see cloud_index_build)
+struct CloudIndex {
+    const float* meta;      // [6] bounding-box low corner, cells per unit length
+    const float* spts;      // [N,3] points in cell order
+    const int32_t* perm;    // [N]   original id of sorted point i
+    const int32_t* start;   // [C+1] first sorted point of each cell
+    const float* cbox;      // [C,6] tight bounding box of each cell's points
+};
 
 namespace {
 
@@ -690,6 +700,278 @@ subsample_reject_kernel(const float* __restrict__ pts, int N, const float* __res
     if (tid == 0) atomicExch(err_flag, 2);
 }
 
+// K3 with a cell index: rejection sampling (see subsample_reject_kernel) whose proposals already follow the weights.
+// The cloud is binned once per shape into kCG^3 cells (points in cell order, a tight box per cell).  Per query, a cell's
+// weight bound wq_c >= max_{i in c} w_i follows from the distance to its box (w is non-increasing in the distance); a
+// proposal picks a cell with probability ~ count_c * wq_c and a point uniformly inside it -- ONE integer drawn uniformly
+// from [0, sum_c count_c * wq_c) gives both -- and is accepted with probability w_i / wq_c.  The probability of proposing and
+// accepting point i is then ~ w_i exactly as for uniform proposals, but ~70 % of the proposals are accepted instead of
+// ~17 % (mean weight on a surface cloud).  The maximum distance (the weights' normalisation) is exact: only cells whose
+// farthest corner beats the best first-point distance are scanned.  Bounds are quantised UP to multiples of 1/65535, so
+// every probability above is an exact integer ratio; 40 random bits select the slot (relative error of a point's
+// probability <= 2e-7).
+constexpr int kCG = 12, kCC = kCG * kCG * kCG;                 // 1728 cells
+constexpr int kCPT = (kCC + kThreads - 1) / kThreads;          // consecutive cells per thread (7)
+
+__global__ void __launch_bounds__(1024) ci_bbox_kernel(const float* __restrict__ pts, int N, float* __restrict__ meta) {
+    __shared__ float red[6][32];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < N; i += 1024)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = pts[i * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+        if ((threadIdx.x & 31) == 0) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        float l = red[a][0], h = red[3 + a][0];
+        for (int w = 1; w < 32; ++w) { l = fminf(l, red[a][w]); h = fmaxf(h, red[3 + a][w]); }
+        meta[a] = l;
+        meta[3 + a] = (h > l) ? (float)kCG / (h - l) : 0.f;
+    }
+}
+
+__device__ __forceinline__ int ci_cell_of(const float* __restrict__ meta, float x, float y, float z) {
+    const int ix = min(kCG - 1, max(0, (int)((x - meta[0]) * meta[3])));
+    const int iy = min(kCG - 1, max(0, (int)((y - meta[1]) * meta[4])));
+    const int iz = min(kCG - 1, max(0, (int)((z - meta[2]) * meta[5])));
+    return (ix * kCG + iy) * kCG + iz;
+}
+
+__global__ void ci_key_kernel(const float* __restrict__ pts, int N, const float* __restrict__ meta, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    key[i] = (uint32_t)ci_cell_of(meta, pts[i * 3 + 0], pts[i * 3 + 1], pts[i * 3 + 2]);
+    val[i] = i;
+}
+
+// one thread per cell: its range in the (stably) sorted order, the points in that order, their tight box
+__global__ void ci_finish_kernel(const float* __restrict__ pts, int N, const uint32_t* __restrict__ key_s, const int32_t* __restrict__ perm,
+                                 int32_t* __restrict__ start, float* __restrict__ spts, float* __restrict__ cbox) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > kCC) return;
+    int lo = 0, hi = N;                       // lower bound of key >= c
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (key_s[mid] < (uint32_t)c) lo = mid + 1; else hi = mid; }
+    start[c] = lo;
+    if (c == kCC) return;
+    float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = lo; i < N && key_s[i] == (uint32_t)c; ++i) {
+        const int id = perm[i];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = pts[id * 3 + a]; spts[i * 3 + a] = v; bl[a] = fminf(bl[a], v); bh[a] = fmaxf(bh[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { cbox[c * 6 + a] = bl[a]; cbox[c * 6 + 3 + a] = bh[a]; }
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+subsample_cells_kernel(const CloudIndex ix, int N, const float* __restrict__ queries, int64_t qbase, const int32_t* __restrict__ qidx, int S,
+                       uint64_t seed, int32_t* __restrict__ out_ids, float* __restrict__ out_pts, int* __restrict__ err_flag) {
+    extern __shared__ int s_first[];             // [N] position of the first accepted proposal of sorted point i
+    __shared__ uint32_t s_prefix[kCC];           // inclusive prefix sums of count_c * wq_c
+    __shared__ uint16_t s_wq[kCC];
+    __shared__ float redf[kThreads / 32];
+    __shared__ uint32_t redu[kThreads / 32];
+    __shared__ int redi[kThreads / 32];
+    __shared__ float s_bcast;
+    __shared__ int s_nfar;
+    int2* s_far = reinterpret_cast<int2*>(s_prefix);      // far-cell list (start, count); the prefix sums are written later
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const float qx = queries[q * 3 + 0], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
+    const uint64_t qi = (uint64_t)(qbase + (qidx ? (int64_t)qidx[q] : q));
+    const float* __restrict__ spts = ix.spts;
+    auto dist2 = [&](int j) {        // float32 like NumPy: (dx*dx + dy*dy) + dz*dz, every operation rounded
+        const float dx = __fsub_rn(qx, spts[j * 3 + 0]), dy = __fsub_rn(qy, spts[j * 3 + 1]), dz = __fsub_rn(qz, spts[j * 3 + 2]);
+        return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    };
+    auto block_max = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();                       // previous readers of redf / s_bcast are done
+        if (lane == 0) redf[warp] = v;
+        __syncthreads();
+        if (tid == 0) { float m = redf[0]; for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, redf[w]); s_bcast = m; }
+        __syncthreads();
+        return s_bcast;
+    };
+    for (int i = tid; i < N; i += kThreads) s_first[i] = 0x7fffffff;
+    // ---- own cells: distance bounds to the box, first-point distance (a lower bound of the maximum distance)
+    const int c0 = tid * kCPT;
+    int cst[kCPT], cnt[kCPT];
+    float dmin2[kCPT], dfar2[kCPT];
+    float lb2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCPT; ++k) {
+        const int c = c0 + k;
+        cst[k] = 0; cnt[k] = 0; dmin2[k] = 0.f; dfar2[k] = 0.f;
+        if (c < kCC) {
+            cst[k] = ix.start[c]; cnt[k] = ix.start[c + 1] - cst[k];
+            if (cnt[k] > 0) {
+                const float* b = ix.cbox + c * 6;
+                const float nx = fmaxf(fmaxf(b[0] - qx, qx - b[3]), 0.f), ny = fmaxf(fmaxf(b[1] - qy, qy - b[4]), 0.f), nz = fmaxf(fmaxf(b[2] - qz, qz - b[5]), 0.f);
+                const float fx = fmaxf(fabsf(qx - b[0]), fabsf(qx - b[3])), fy = fmaxf(fabsf(qy - b[1]), fabsf(qy - b[4])), fz = fmaxf(fabsf(qz - b[2]), fabsf(qz - b[5]));
+                dmin2[k] = nx * nx + ny * ny + nz * nz;
+                dfar2[k] = fx * fx + fy * fy + fz * fz;
+                lb2 = fmaxf(lb2, dist2(cst[k]));
+            }
+        }
+    }
+    if (tid == 0) s_nfar = 0;
+    const float best_lb2 = block_max(lb2);
+    // ---- exact maximum distance: only cells whose farthest corner can beat the best first-point distance.  The distance to
+    // the far side of a surface is flat, so this is still a fifth of the cloud: the cells go to a shared list and are scanned
+    // a warp per cell, four cells in flight (a thread walking its own cells was one dependent gather after the other).
+    constexpr int kFarCap = kCC / 2;                  // int2 entries that fit into the prefix array
+    float m2 = lb2;
+#pragma unroll
+    for (int k = 0; k < kCPT; ++k)
+        if (cnt[k] > 1 && dfar2[k] * 1.00001f >= best_lb2) {
+            const int slot = atomicAdd(&s_nfar, 1);
+            if (slot < kFarCap) s_far[slot] = make_int2(cst[k] + 1, cnt[k] - 1);        // (the first point is already in lb2)
+            else for (int j = cst[k] + 1; j < cst[k] + cnt[k]; ++j) m2 = fmaxf(m2, dist2(j));   // list full: scan in place
+        }
+    __syncthreads();
+    {
+        const int L = min(s_nfar, kFarCap);
+        for (int it = warp * 4; it < L; it += (kThreads / 32) * 4) {
+            int2 rg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rg[u] = (it + u < L) ? s_far[it + u] : make_int2(0, 0);
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (lane < rg[u].y) d[u] = dist2(rg[u].x + lane);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                m2 = fmaxf(m2, d[u]);
+                for (int j = lane + 32; j < rg[u].y; j += 32) m2 = fmaxf(m2, dist2(rg[u].x + j));     // cells with more than 32 points
+            }
+        }
+    }
+    const float dmax = __fsqrt_rn(block_max(m2));    // max of float32 norms = sqrt of the max float32 squared sum (sqrt is monotone)
+    auto weight_of = [&](float d) {                  // dist_prob (utils.py:200-208), float32 like NumPy; non-increasing in d
+        return fminf(fmaxf(__fsub_rn(1.0f, __fmul_rn(1.5f, __fdiv_rn(d, dmax))), 0.05f), 1.0f);
+    };
+    // ---- cell weights (bounds rounded UP to multiples of 1/65535) and their prefix sums
+    uint32_t wsum = 0, wq[kCPT];
+#pragma unroll
+    for (int k = 0; k < kCPT; ++k) {
+        wq[k] = 0;
+        if (cnt[k] > 0) {
+            const float wmax = weight_of(sqrtf(dmin2[k]) * 0.99999f);     // distance to the box, shrunk: a safe lower bound of every d_i
+            wq[k] = min(65535u, (uint32_t)ceilf(wmax * 65535.0f) + 1u);
+            wsum += (uint32_t)cnt[k] * wq[k];
+        }
+    }
+    uint32_t incl = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) redu[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - wsum, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { const uint32_t c = redu[w]; if (w < warp) run += c; total += c; }
+#pragma unroll
+    for (int k = 0; k < kCPT; ++k) {
+        const int c = c0 + k;
+        if (c < kCC) { run += (uint32_t)cnt[k] * wq[k]; s_prefix[c] = run; s_wq[c] = (uint16_t)wq[k]; }
+    }
+    __syncthreads();
+    // ---- proposal rounds (same protocol as subsample_reject_kernel)
+    int base = 0, pos0 = 0, per = 6;
+    for (int round = 0; round < kRejRounds; ++round) {
+        const int mypos = pos0 + tid * per;
+        int idx[kRejPer];
+        unsigned acc = 0;
+        // The proposals of a thread are processed in lock step, phase by phase, so that their shared-memory searches and their
+        // gathers overlap (one proposal after the other was a chain of ~15 dependent memory accesses each).
+        uint32_t xs[kRejPer];
+        float us[kRejPer];
+#pragma unroll
+        for (int e2 = 0; e2 < kRejPer / 2; ++e2) {
+            uint32_t r[4] = {0u, 0u, 0u, 0u};
+            if (2 * e2 < per)
+                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)((mypos >> 1) + e2), 0x85ebca6bu, r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // 40 random bits -> slot x in [0, total)
+                const unsigned long long x40 = ((unsigned long long)r[2 * h] << 32) | ((unsigned long long)(r[2 * h + 1] & 0xffu) << 24);
+                xs[2 * e2 + h] = (uint32_t)__umul64hi(x40, (unsigned long long)total);
+                us[2 * e2 + h] = (2 * e2 < per) ? (float)(r[2 * h + 1] >> 8) * (1.0f / 16777216.0f) : 1e30f;    // [0, 1); 1e30 = never accepted
+            }
+        }
+        int cel[kRejPer];          // number of prefix sums <= x  =  smallest cell with s_prefix[c] > x
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) cel[e] = 0;
+#pragma unroll
+        for (int step = 1024; step >= 1; step >>= 1) {
+#pragma unroll
+            for (int e = 0; e < kRejPer; ++e) {
+                const int np = cel[e] + step;
+                if (np <= kCC && s_prefix[np - 1] <= xs[e]) cel[e] = np;
+            }
+        }
+        float wqf[kRejPer];
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) {
+            const int c = cel[e];
+            const uint32_t wqc = s_wq[c];
+            const uint32_t off = xs[e] - (c ? s_prefix[c - 1] : 0u);
+            idx[e] = ix.start[c] + (int)(off / wqc);
+            wqf[e] = (float)wqc * (1.0f / 65535.0f);
+        }
+        float d2[kRejPer];
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) d2[e] = dist2(idx[e]);
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) {
+            const float w = weight_of(__fsqrt_rn(d2[e]));
+            if (us[e] * wqf[e] < w) { acc |= 1u << e; atomicMin(&s_first[idx[e]], mypos + e); }
+        }
+        __syncthreads();
+        unsigned fresh = 0;
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e)
+            if (((acc >> e) & 1u) && s_first[idx[e]] == mypos + e) fresh |= 1u << e;
+        const int cntf = __popc(fresh);
+        int inc = cntf;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) redi[warp] = inc;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { const int c = redi[w]; if (w < warp) wbase += c; tot += c; }
+        int slot = base + wbase + inc - cntf;
+#pragma unroll
+        for (int e = 0; e < kRejPer; ++e) {
+            if ((fresh >> e) & 1u) {
+                if (slot < S) {
+                    const int j = idx[e];
+                    out_ids[q * S + slot] = ix.perm[j];
+                    if (out_pts) {
+                        float* o = out_pts + (q * S + slot) * 3;
+                        o[0] = spts[j * 3 + 0]; o[1] = spts[j * 3 + 1]; o[2] = spts[j * 3 + 2];
+                    }
+                }
+                ++slot;
+            }
+        }
+        base += tot;
+        if (base >= S) return;
+        pos0 += kThreads * per;
+        const long long need = ((long long)(S - base) * (kThreads * per) * 23 / 20) / (tot > 0 ? tot : 1) + 1;
+        const long long p2 = (need + 2 * kThreads - 1) / (2 * kThreads);
+        per = (int)(p2 < 1 ? 1 : (p2 > kRejPer / 2 ? kRejPer / 2 : p2)) * 2;
+        __syncthreads();
+    }
+    if (tid == 0) atomicExch(err_flag, 2);
+}
+
 __global__ void gather_points_kernel(const float* __restrict__ pts, const int32_t* __restrict__ ids, int64_t count, float* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -758,10 +1040,50 @@ void ball_patch(const float* pts, int64_t N, const float* queries, int64_t Q, in
                (float)patch_radius, seed, ids, patch, radius, counts, err_flag_dev());
 }
 
+// Cell index of a cloud for the weighted sub-sampler: bounding box -> cell keys -> stable radix sort (points of a cell keep
+// their id order, so the result is deterministic) -> per-cell ranges, sorted points, tight boxes.  The index lives in a
+// thread-local workspace and is valid until the next call on this thread (stream order).
+bool cloud_index_usable(int64_t N, int S, int mode) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("P2S_SUBSAMPLE_NOCELLS"); off = (e && e[0] == '1') ? 1 : 0; }
+    return !off && mode == P2S_SUBSAMPLE_WEIGHTED && N >= 2 * (int64_t)S && (size_t)N * 4 <= 150 * 1024;
+}
+
+const CloudIndex* cloud_index_build(const float* pts, int64_t N, cudaStream_t st) {
+    static thread_local DevBuf ws;
+    static thread_local CloudIndex ci;
+    const int n = (int)N;
+    size_t cub_bytes = 0;
+    P2S_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 11, st));
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t o_meta = off; off += al(6 * 4);
+    const size_t o_key = off; off += al((size_t)n * 4);
+    const size_t o_val = off; off += al((size_t)n * 4);
+    const size_t o_keys = off; off += al((size_t)n * 4);
+    const size_t o_perm = off; off += al((size_t)n * 4);
+    const size_t o_start = off; off += al((size_t)(kCC + 1) * 4);
+    const size_t o_spts = off; off += al((size_t)n * 12);
+    const size_t o_cbox = off; off += al((size_t)kCC * 24);
+    const size_t o_cub = off; off += al(cub_bytes);
+    uint8_t* b = (uint8_t*)ws.get(off);
+    float* meta = (float*)(b + o_meta);
+    uint32_t* key = (uint32_t*)(b + o_key); int32_t* val = (int32_t*)(b + o_val);
+    uint32_t* key_s = (uint32_t*)(b + o_keys); int32_t* perm = (int32_t*)(b + o_perm);
+    P2S_LAUNCH(ci_bbox_kernel, 1, 1024, 0, st, pts, n, meta);
+    P2S_LAUNCH(ci_key_kernel, (unsigned)cdiv(n, 256), 256, 0, st, pts, n, meta, key, val);
+    P2S_CUDA(cub::DeviceRadixSort::SortPairs(b + o_cub, cub_bytes, key, key_s, val, perm, n, 0, 11, st));    // kCC = 1728 < 2^11
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    P2S_LAUNCH(ci_finish_kernel, (unsigned)cdiv(kCC + 1, 128), 128, 0, st, pts, n, key_s, perm, (int32_t*)(b + o_start), (float*)(b + o_spts), (float*)(b + o_cbox));
+    ci.meta = meta; ci.spts = (const float*)(b + o_spts); ci.perm = perm; ci.start = (const int32_t*)(b + o_start); ci.cbox = (const float*)(b + o_cbox);
+    return &ci;
+}
+
 // the Philox stream of query q is keyed by qbase + (qidx ? qidx[q] : q).  pts_out (optional): [Q, S, 3] the selected
-// points themselves (what gather_points would produce from `out`).
+// points themselves (what gather_points would produce from `out`).  cidx (optional): the cloud's cell index (built here if
+// the cell sampler applies and none is given).
 void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int64_t qbase, int S,
-               int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx, float* pts_out) {
+               int mode, uint64_t seed, int32_t* out, cudaStream_t st, const int32_t* qidx, float* pts_out, const CloudIndex* cidx) {
     P2S_CHECK(N >= S, "sub-sample needs N >= sub_sample_size (reference zero-pads after an in-place shuffle; unsupported)");
     P2S_CHECK(N < (1 << 30), "cloud too large");
     if (Q <= 0) return;
@@ -773,7 +1095,16 @@ void subsample(const float* pts, int64_t N, const float* queries, int64_t Q, int
         const size_t cache_bytes = (size_t)N * sizeof(float);
         static int no_reject = -1;
         if (no_reject < 0) { const char* e = getenv("P2S_SUBSAMPLE_CLOCKS"); no_reject = (e && e[0] == '1') ? 1 : 0; }
-        if (cache_bytes <= 160 * 1024 && N >= 2 * (int64_t)S && !no_reject) {
+        if (cloud_index_usable(N, S, mode) && !no_reject) {
+            if (!cidx) cidx = cloud_index_build(pts, N, st);
+            static thread_local bool attr_set = false;
+            if (!attr_set) {
+                P2S_CUDA(cudaFuncSetAttribute(subsample_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+                attr_set = true;
+            }
+            P2S_LAUNCH(subsample_cells_kernel, (unsigned)Q, kThreads, cache_bytes, st, *cidx, (int)N, queries, qbase, qidx, S, seed, out, pts_out, err_flag_dev());
+            gathered = true;
+        } else if (cache_bytes <= 160 * 1024 && N >= 2 * (int64_t)S && !no_reject) {
             // rejection sampling: cheap when at most half of the cloud is drawn (the acceptance rate is >= 0.05 by construction)
             static thread_local bool attr_set = false;
             if (!attr_set) {
