@@ -173,6 +173,53 @@ def test_subsample_weighted_is_without_replacement_and_matches_reference_law():
     assert freq_gpu[near[:10]].mean() > freq_gpu[near[-10:]].mean() + 0.1
 
 
+_SAMPLER_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import p2s_oracle as orc
+from points2surf_b200 import ops, synth
+dev = 'cuda:0'
+cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+# (a) law on a small cloud: inclusion frequencies vs RandomState.choice(replace=False, p)
+rng = np.random.RandomState(3)
+cloud = rng.uniform(-0.9, 0.9, (40, 3)).astype(np.float32)
+qp = np.array([[0.3, -0.2, 0.1]], np.float32)
+trials = 4000
+ids = ops.subsample(cu(cloud), cu(np.repeat(qp, trials, axis=0)), 10, False, seed=11).cpu().numpy()
+assert all(len(set(r.tolist())) == 10 for r in ids)
+freq = np.bincount(ids.ravel(), minlength=40) / trials
+prob = orc.sub_sample_probabilities(cloud, qp[0])
+rs = np.random.RandomState(5)
+ref = np.stack([rs.choice(40, size=10, replace=False, p=prob) for _ in range(trials)])
+dev_max = np.abs(freq - np.bincount(ref.ravel(), minlength=40) / trials).max()
+assert dev_max < 0.05, dev_max
+# (b) a surface cloud at the benchmark's sizes: distinct ids in range, near points favoured, slabs reproduce the whole
+cloud = synth.make_cloud('sphere', 10000, seed=0)
+q = cloud[:64] * np.float32(0.97)
+a = ops.subsample(cu(cloud), cu(q), 1000, False, seed=7).cpu().numpy()
+assert a.min() >= 0 and a.max() < 10000 and all(len(set(r.tolist())) == 1000 for r in a)
+b = ops.subsample(cu(cloud), cu(q[10:20]), 1000, False, seed=7, query_index_base=10).cpu().numpy()
+assert np.array_equal(np.sort(a[10:20], axis=1), np.sort(b, axis=1))
+d = np.linalg.norm(cloud[a[0]] - q[0], axis=1)
+assert d.mean() < np.linalg.norm(cloud - q[0], axis=1).mean()
+print('sampler ok', dev_max)
+"""
+
+
+@pytest.mark.parametrize('env', [{}, {'P2S_SUBSAMPLE_NOCELLS': '1'}, {'P2S_SUBSAMPLE_CLOCKS': '1'}])
+def test_subsample_weighted_all_three_kernels_realise_the_reference_law(env):
+    # the cell-index sampler (default), the uniform-proposal rejection sampler and the exponential-clock selection are
+    # switched by environment variables that the library reads once per process -> one subprocess per kernel
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, '-c', _SAMPLER_SCRIPT % root], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'sampler ok' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_subsample_requires_enough_points():
     cloud = synth.make_cloud('sphere', 100, seed=1)
     with pytest.raises(ops.P2SError):
