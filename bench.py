@@ -173,6 +173,10 @@ def run_reference(args):
                                    % (args.cpu_sample, r['Q'], r['workers'], r['threads'])},
         'e2e': {'value': value, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if world > 1:
+        # the CPU arm does not scale with --gpus: one host, rank 0 alone ran (the other ranks exited without work)
+        line['cpu_baseline']['hosts'] = 1
+        line['cpu_baseline']['sample'] += '; launched with %d ranks: rank 0 alone ran on this single host' % world
     print(json.dumps(line))
 
 
