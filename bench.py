@@ -475,14 +475,21 @@ def run_b200(args):
     sharded_job = tile_sharded = None
     if not args.skip_sharded:
         # config 3 analogue (max model, mixed shapes, LPT, whole pipeline + mesh gather timed) and strong scaling of one shape
-        sharded_job = run_sharded_job('max', args.shapes_per_gpu, args.grid_res, args.epsilon, args.seed, args.points, precision, guard,
-                                      rank, world, dev, dist)
-        sd_fit = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4, fitted=True)
-        eng_fit = ops.Engine(sd_fit, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
-        pts0 = torch.from_numpy(synth.make_cloud('sphere', args.points, seed=0)).to(dev)     # the same shape on every rank
-        Q0 = int(ops.query_grid(pts0, args.grid_res, args.epsilon).numel())
-        tile_sharded = run_tile_sharded(eng_fit, pts0, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, Q0, rank, world, dev, dist)
-        eng_fit.close()
+        # (a failure in these add-on sections must not take the headline line with it: it is reported in their place)
+        try:
+            sharded_job = run_sharded_job('max', args.shapes_per_gpu, args.grid_res, args.epsilon, args.seed, args.points, precision, guard,
+                                          rank, world, dev, dist)
+        except Exception as e:  # noqa: BLE001
+            sharded_job = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            sd_fit = synth.make_state_dict(args.model, 6 if args.model == 'vanilla' else 4, fitted=True)
+            eng_fit = ops.Engine(sd_fit, v['use_point_stn'], v['shared_transformer'], device=local_rank, precision=precision, guard_band=guard)
+            pts0 = torch.from_numpy(synth.make_cloud('sphere', args.points, seed=0)).to(dev)     # the same shape on every rank
+            Q0 = int(ops.query_grid(pts0, args.grid_res, args.epsilon).numel())
+            tile_sharded = run_tile_sharded(eng_fit, pts0, args.grid_res, args.epsilon, v['uniform_subsample'], args.seed, Q0, rank, world, dev, dist)
+            eng_fit.close()
+        except Exception as e:  # noqa: BLE001
+            tile_sharded = {'error': '%s: %s' % (type(e).__name__, e)}
     e2e_ms, _ = timed(step_host, args.steps, 1, host=True)
     guard_frac = guard_total / max(Q * (args.steps + max(args.warmup, 3)), 1)
 
