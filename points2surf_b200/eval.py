@@ -75,6 +75,8 @@ def _check_supported(train_opt, eval_opt):
         raise ValueError('Unsupported symmetric operation: %s' % train_opt.sym_op)
     if getattr(train_opt, 'single_transformer', 0):
         raise ValueError('Unsupported option: single_transformer=1')
+    if getattr(train_opt, 'fixed_subsample', 0) and not getattr(train_opt, 'uniform_subsample', 0):
+        raise ValueError('Unsupported option: fixed_subsample=1 with the distance-weighted sub-sample (only with uniform_subsample=1)')
     if eval_opt.sampling not in ('full', 'sequential_shapes_random_patches'):
         raise ValueError('Unknown sampling strategy: %s' % eval_opt.sampling)
     if eval_opt.sampling != 'full' and eval_opt.reconstruction:
@@ -120,18 +122,48 @@ def _rotate_inputs(patch, sub, q, R):
             torch.matmul(q.unsqueeze(1), Rt).squeeze(1).contiguous())
 
 
+def _fixed_sub(pts_dev, n, sub_sample_size):
+    """[n,S,3]: the one fixed uniform sub-sample of the shape, for every query (samplers.fixed_uniform_subsample_ids)."""
+    ids = torch.from_numpy(samplers.fixed_uniform_subsample_ids(pts_dev.shape[0], sub_sample_size).astype(np.int64)).to(pts_dev.device)
+    return pts_dev.index_select(0, ids).unsqueeze(0).expand(n, -1, -1).contiguous()
+
+
+def _patches(pts_dev, q, train_opt, seed, query_index_base=0):
+    """-> (patch_pts_ps [n,P,3], radius [n] or None for fixed-radius patches)."""
+    patch_radius = float(getattr(train_opt, 'patch_radius', 0.0))
+    if patch_radius > 0.0:       # radius ablations: ball query, fixed-radius normalisation, |d| not rescaled (eval.py:364-368)
+        _, patch, _, _ = ops.ball_patch(pts_dev, q, train_opt.points_per_patch, patch_radius, seed, query_index_base=query_index_base)
+        return patch, None
+    _, patch, radius = ops.knn_patch(pts_dev, q, train_opt.points_per_patch)
+    return patch, radius
+
+
+def _reconstruct_fixed_subsample(eng, train_opt, eval_opt, pts_dev):
+    """Reconstruction pass of a model trained with --fixed_subsample 1 (uniform): the fused pipeline draws a sub-sample per
+    query, so this variant runs stage by stage -- candidate grid, patches, the ONE fixed sub-sample, network, post-process."""
+    lin = ops.query_grid(pts_dev, eval_opt.query_grid_resolution, eval_opt.epsilon)
+    q_all = ops.query_points(lin, eval_opt.query_grid_resolution)
+    bs = eval_opt.batchSize if eval_opt.batchSize > 0 else 4096
+    out = []
+    for b0 in range(0, q_all.shape[0], bs):
+        q = q_all[b0:b0 + bs].contiguous()
+        patch, radius = _patches(pts_dev, q, train_opt, eval_opt.seed, query_index_base=b0)
+        sub = _fixed_sub(pts_dev, q.shape[0], train_opt.sub_sample_size)
+        out.append(ops.sdf_from_logits(eng.forward(patch, sub, q), radius))
+    sdf = torch.cat(out) if out else torch.zeros((0,), dtype=torch.float32, device=pts_dev.device)
+    return lin, sdf
+
+
 def _eval_given_queries(eng, train_opt, eval_opt, pts_dev, query_pts, dev):
     """Non-reconstruction pass (full_eval.py:31-41): queries from 05_query_pts, random rotation augmentation
     of patch / sub-sample / query like the reference's dataset does when reconstruction is False."""
     q = torch.from_numpy(np.ascontiguousarray(query_pts, dtype=np.float32)).to(dev)
-    patch_radius = float(getattr(train_opt, 'patch_radius', 0.0))
-    if patch_radius > 0.0:       # radius ablations: ball query, fixed-radius normalisation, |d| not rescaled (eval.py:364-368)
-        _, patch, _, _ = ops.ball_patch(pts_dev, q, train_opt.points_per_patch, patch_radius, eval_opt.seed)
-        radius = None
-    else:
-        _, patch, radius = ops.knn_patch(pts_dev, q, train_opt.points_per_patch)
+    patch, radius = _patches(pts_dev, q, train_opt, eval_opt.seed)
     uniform = bool(getattr(train_opt, 'uniform_subsample', 0))
-    sub = ops.gather_points(pts_dev, ops.subsample(pts_dev, q, train_opt.sub_sample_size, uniform, eval_opt.seed))
+    if getattr(train_opt, 'fixed_subsample', 0):
+        sub = _fixed_sub(pts_dev, q.shape[0], train_opt.sub_sample_size)
+    else:
+        sub = ops.gather_points(pts_dev, ops.subsample(pts_dev, q, train_opt.sub_sample_size, uniform, eval_opt.seed))
     R = torch.from_numpy(_random_rotations(np.random.RandomState(eval_opt.seed), q.shape[0])).to(dev)
     patch, sub, qr = _rotate_inputs(patch, sub, q, R)
     out = []
@@ -194,7 +226,10 @@ def points_to_surf_eval(eval_opt):
                 continue
             pts = _load_pts(eval_opt.indir, name)
             pts_dev = torch.from_numpy(pts).to(dev)
-            if eval_opt.reconstruction:
+            if eval_opt.reconstruction and getattr(train_opt, 'fixed_subsample', 0):
+                lin, sdf = _reconstruct_fixed_subsample(eng, train_opt, eval_opt, pts_dev)
+                query_pts = ops.query_points(lin, eval_opt.query_grid_resolution).cpu().numpy()
+            elif eval_opt.reconstruction:
                 lin, sdf = eng.reconstruct(pts_dev, eval_opt.query_grid_resolution, eval_opt.epsilon, uniform,
                                            eval_opt.seed, batch=eval_opt.batchSize,
                                            patch_radius=float(getattr(train_opt, 'patch_radius', 0.0)))

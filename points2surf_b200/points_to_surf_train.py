@@ -55,7 +55,7 @@ def parse_arguments(args=None):
     p.add_argument('--seed', type=int, default=3627473, help='manual seed')
     p.add_argument('--single_transformer', type=int, default=0, help='0: two transformers, 1: unsupported here')
     p.add_argument('--uniform_subsample', type=int, default=0, help='1: uniform global sub-sample, 0: distance-dependent')
-    p.add_argument('--fixed_subsample', type=int, default=0, help='1: same fixed sub-sample for all patches (unsupported here)')
+    p.add_argument('--fixed_subsample', type=int, default=0, help='1: same fixed sub-sample for all patches (with --uniform_subsample 1 only)')
     p.add_argument('--shared_transformer', type=int, default=0, help='single shared QSTN for the local and global point sets')
     p.add_argument('--training_order', type=str, default='random', help='random | random_shape_consecutive')
     p.add_argument('--identical_epochs', type=int, default=False, help='use same patches in each epoch, mainly for debugging')
@@ -103,8 +103,8 @@ def _check_supported(opt):
         raise ValueError('Unsupported option: single_transformer=1')
     if not opt.use_feat_stn:
         raise ValueError('Unsupported option: use_feat_stn=0')
-    if opt.fixed_subsample:
-        raise ValueError('Unsupported option: fixed_subsample=1')
+    if opt.fixed_subsample and not opt.uniform_subsample:
+        raise ValueError('Unsupported option: fixed_subsample=1 with the distance-weighted sub-sample (only with uniform_subsample=1)')
     if opt.training_order not in ('random', 'random_shape_consecutive'):
         raise ValueError('Unknown training order: %s' % opt.training_order)
     if opt.use_point_stn and not (opt.shared_transformer in (0, 1, False, True)):
@@ -153,11 +153,12 @@ class GpuAssembler:
     """kNN patch + radius + patch-space normalisation and the global sub-sample of a group of query points of one shape,
     on the device (the call sequence of points2surf_b200.eval._eval_given_queries)."""
 
-    def __init__(self, device, points_per_patch, sub_sample_size, uniform_subsample, seed, patch_radius=0.0):
+    def __init__(self, device, points_per_patch, sub_sample_size, uniform_subsample, seed, patch_radius=0.0, fixed_subsample=False):
         from . import ops
         self.ops, self.device = ops, device
         self.P, self.S, self.uniform, self.seed = points_per_patch, sub_sample_size, bool(uniform_subsample), int(seed)
         self.patch_radius = float(patch_radius)          # > 0: ball-query patches of a fixed radius (radius ablations)
+        self.fixed = bool(fixed_subsample)               # --fixed_subsample 1: the same uniform ids for every query of a shape
         self._clouds = {}
         self.calls = 0
 
@@ -177,6 +178,10 @@ class GpuAssembler:
             _, patch, radius, _ = self.ops.ball_patch(pts_dev, q, self.P, self.patch_radius, self.seed + self.calls)
         else:
             _, patch, radius = self.ops.knn_patch(pts_dev, q, self.P)
+        if self.fixed:
+            from .samplers import fixed_uniform_subsample_ids
+            ids = torch.from_numpy(fixed_uniform_subsample_ids(pts_dev.shape[0], self.S).astype(np.int64)).to(self.device)
+            return patch, radius, pts_dev.index_select(0, ids).unsqueeze(0).expand(q.shape[0], -1, -1).contiguous(), q
         ids = self.ops.subsample(pts_dev, q, self.S, self.uniform, self.seed + self.calls)   # a fresh Philox stream per call
         return patch, radius, self.ops.gather_points(pts_dev, ids), q
 
@@ -347,7 +352,7 @@ def points_to_surf_train(opt, prims=None, assembler=None, device=None, dtype=tor
                    output_loss_weights=output_loss_weights, fixed_radius=opt.patch_radius > 0.0, dtype=dtype)
     if assembler is None:
         assembler = GpuAssembler(device, opt.points_per_patch, opt.sub_sample_size, opt.uniform_subsample, opt.seed + rank,
-                                 patch_radius=opt.patch_radius)
+                                 patch_radius=opt.patch_radius, fixed_subsample=opt.fixed_subsample)
     rng_aug = np.random.RandomState(opt.seed + rank)            # augmentation / sub-sample streams differ per rank
 
     if is_main:

@@ -78,3 +78,12 @@ class RandomPointcloudPatchSampler:
 
     def __len__(self):
         return self.total_patch_count
+
+
+def fixed_uniform_subsample_ids(num_points, sub_sample_size):
+    """`--fixed_subsample 1` with `--uniform_subsample 1` (experiments/train_p2s_vanilla_uniform_subsample.sh):
+    utils.get_point_cloud_sub_sample re-seeds its RandomState with 42 before every draw (source/base/utils.py:210-216), so every
+    query of a shape gets the SAME ids, `RandomState(42).randint(0, N, S)` -- reproduced here bit for bit, stream included."""
+    if num_points < sub_sample_size:
+        raise ValueError('sub-sample needs N >= sub_sample_size (the reference zero-pads after an in-place shuffle; unsupported)')
+    return np.random.RandomState(42).randint(low=0, high=num_points, size=sub_sample_size)

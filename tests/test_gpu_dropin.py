@@ -107,6 +107,40 @@ def test_radius_ablation_checkpoint_reconstructs(tmp_path):
     assert np.isfinite(d).all() and np.abs(d).max() <= 1.0        # tanh^2, not rescaled by a radius (eval.py:364-368)
 
 
+def test_fixed_uniform_subsample_checkpoint_reconstructs_like_the_reference(tmp_path):
+    """train_opt.fixed_subsample = 1 with uniform_subsample = 1 (experiments/train_p2s_vanilla_uniform_subsample.sh): every query of a
+    shape sees the sub-sample pts[RandomState(42).randint(0, N, S)] (utils.py:210-216).  The eval entry point runs this variant
+    stage by stage; a few queries are replayed on the CPU oracle with exactly those ids (fp32 engine, same tolerance as the
+    fused-pipeline replay)."""
+    root, models, sd = _make_dataset(tmp_path)
+    opt_ns = synth.make_train_opt('vanilla')
+    opt_ns.uniform_subsample = 1
+    opt_ns.fixed_subsample = 1
+    torch.save(opt_ns, models / 'p2s_test_params.pth')
+    res, eps = 16, 3
+    opt = p2s_eval.parse_arguments(['--indir', str(root), '--outdir', str(tmp_path / 'r'), '--modeldir', str(models), '--models', 'p2s_test',
+                                    '--query_grid_resolution', str(res), '--epsilon', str(eps), '--precision', 'fp32', '--batchSize', '300'])
+    opt.reconstruction = True
+    p2s_eval.points_to_surf_eval(opt)
+    cloud = load_golden('assembly.npz')['cloud'][:, :3].astype(np.float32)
+    qpts = orc.query_grid(cloud, res, eps)
+    assert np.array_equal(np.load(tmp_path / 'r' / 'rec' / 'query_pts_ms' / 'shape_a.xyz.npy'), qpts)
+    d = np.load(tmp_path / 'r' / 'rec' / 'dist_ms' / 'shape_a.xyz.npy')
+    assert d.shape == (len(qpts),) and np.isfinite(d).all()
+    ids = np.random.RandomState(42).randint(low=0, high=len(cloud), size=1000)
+    sel = [0, 1, len(qpts) // 2, len(qpts) - 1]
+    kd = orc.make_kdtree(cloud)
+    patches, radii = zip(*[(orc.knn_patch(cloud, kd, qpts[i], 300)[1:]) for i in sel])
+    sub = np.repeat(cloud[ids][None], len(sel), axis=0)
+    logits = orc.model_forward(sd, np.stack(patches), sub, qpts[sel], True, True)
+    np.testing.assert_allclose(d[sel], orc.post_process(logits, np.array(radii)), rtol=0, atol=2e-4)
+    # the distance-weighted sub-sample has no fixed variant here
+    opt_ns.uniform_subsample = 0
+    torch.save(opt_ns, models / 'p2s_test_params.pth')
+    with pytest.raises(ValueError):
+        p2s_eval.points_to_surf_eval(opt)
+
+
 def test_unsupported_options_raise(tmp_path):
     root, models, _ = _make_dataset(tmp_path)
     opt_ns = synth.make_train_opt('vanilla')

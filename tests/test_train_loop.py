@@ -105,6 +105,8 @@ def test_unsupported_training_options_raise():
     base = ['--outputs', 'imp_surf_magnitude', 'imp_surf_sign', '--patch_radius', '0.0']
     p2s_train._check_supported(p2s_train.parse_arguments(base))
     p2s_train._check_supported(p2s_train.parse_arguments(base + ['--patch_radius', '0.1']))     # radius ablations: ball-query patches
+    # train_p2s_vanilla_uniform_subsample.sh: the fixed sub-sample is supported together with the uniform one only
+    p2s_train._check_supported(p2s_train.parse_arguments(base + ['--uniform_subsample', '1', '--fixed_subsample', '1']))
     for extra in (['--sym_op', 'sum'], ['--single_transformer', '1'], ['--training_order', 'bogus'],
                   ['--fixed_subsample', '1'], ['--outputs', 'imp_surf'], ['--outputs', 'normals']):
         with pytest.raises(ValueError):
